@@ -1,0 +1,168 @@
+/*
+ * zvdb_b200.h -- C ABI of libzvdb_b200.so: the B200 (sm_100a) implementation of zvdb's HNSW
+ * search hot path.
+ *
+ * The reference (allisoneer/zvdb) has no FFI of its own: its boundary is the Zig generic type
+ * `HNSW(T)` in src/hnsw.zig, re-exported by src/zvdb.zig:1. These entry points are what a Zig
+ * `extern fn` block behind that type binds (see INTEGRATION.md for the wrapper source); each
+ * one names the reference interface it replaces. Plain pointers and sizes only: no C++ types,
+ * no torch types. All functions return a zvdb_status (0 = ok) unless noted; on failure
+ * zvdb_last_error() holds a message for the calling thread.
+ *
+ * There is NO CPU fallback: every search runs in the CUDA kernels of this library, and every
+ * call fails with ZVDB_ERR_CUDA if no sm_100 device is usable.
+ *
+ * Threading: like the reference (one global mutex around insert and search, hnsw.zig:74-75,
+ * :195-196) every call on a handle takes the handle's mutex, so a handle may be shared between
+ * threads. The parallel path is the batch call, not concurrent single searches.
+ */
+#ifndef ZVDB_B200_H
+#define ZVDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ZVDB_API __attribute__((visibility("default")))
+#else
+#define ZVDB_API
+#endif
+
+typedef struct zvdb_index zvdb_index; /* opaque; replaces the `HNSW(f32)` struct, hnsw.zig:44-50 */
+
+typedef enum zvdb_status {
+    ZVDB_OK = 0,
+    ZVDB_ERR_OUT_OF_MEMORY = 1,  /* Zig error.OutOfMemory (every `try` in hnsw.zig) */
+    ZVDB_ERR_NODE_NOT_FOUND = 2, /* Zig error.NodeNotFound, hnsw.zig:120-121 */
+    ZVDB_ERR_DIM_MISMATCH = 3,   /* the reference @panics, hnsw.zig:183-185; here it is an error */
+    ZVDB_ERR_CUDA = 4,           /* no device / kernel or copy failure; there is no CPU fallback */
+    ZVDB_ERR_INVALID = 5,        /* null pointer, k == 0 with outputs, bad enum ... */
+    ZVDB_ERR_UNSUPPORTED = 6     /* shape outside what the kernels are built for (message says which) */
+} zvdb_status;
+
+typedef enum zvdb_metric {
+    ZVDB_METRIC_L2 = 0,     /* squared L2: the reference's only metric, hnsw.zig:182-192 */
+    ZVDB_METRIC_COSINE = 1, /* extension: 1 - dot on rows L2-normalised at insert */
+    ZVDB_METRIC_DOT = 2     /* extension: -dot */
+} zvdb_metric;
+
+#define ZVDB_INVALID_ID UINT64_MAX
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+/* HNSW(T).init(allocator, m, ef_construction), hnsw.zig:52-62. `dim` may be 0: it is then fixed
+ * by the first insert, as in the reference (which stores no dim). `ef_construction` is stored
+ * and, as in the reference, never read (hnsw.zig:49,59). `device` is a CUDA ordinal. */
+ZVDB_API int zvdb_create(zvdb_index **out, uint32_t dim, uint32_t m, uint32_t ef_construction,
+                         int metric, int device);
+
+/* HNSW(T).deinit, hnsw.zig:64-71. Invalidates every pointer returned by zvdb_get_point. */
+ZVDB_API void zvdb_destroy(zvdb_index *ix);
+
+/* Seed of the level generator that stands in for std.crypto.random (hnsw.zig:172-180).
+ * Layer 0, the only layer search reads (hnsw.zig:216), does not depend on it. */
+ZVDB_API int zvdb_set_level_seed(zvdb_index *ix, uint64_t seed);
+
+/* ---- insert (graph producer) ------------------------------------------------------------ */
+
+/* HNSW(T).insert(point), hnsw.zig:73-117 (+ connect :119-141, shrinkConnections :143-170).
+ * Ids are 0,1,2,... in call order (hnsw.zig:77). The point is copied (hnsw.zig:24-26). The
+ * graph update runs on the host in the reference's order and arithmetic; the device copy is
+ * refreshed lazily by the next search. */
+ZVDB_API int zvdb_insert(zvdb_index *ix, const float *point, uint32_t dim);
+
+/* n successive zvdb_insert calls on rows of a [n x dim] array, one lock acquisition.
+ * `levels` (may be NULL) forces each node's level instead of drawing it: test hook. */
+ZVDB_API int zvdb_insert_batch(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim,
+                               const int32_t *levels);
+
+/* hnsw.nodes.count(), the one field the reference's tests read (test_hnsw.zig:198). */
+ZVDB_API uint64_t zvdb_count(const zvdb_index *ix);
+ZVDB_API uint32_t zvdb_dim(const zvdb_index *ix);
+ZVDB_API uint32_t zvdb_max_level(const zvdb_index *ix);   /* hnsw.zig:47 */
+ZVDB_API int64_t zvdb_entry_point(const zvdb_index *ix);  /* hnsw.zig:46; -1 = null */
+
+/* Node.point of node `id` (hnsw.zig:14): `dim` floats owned by the index, valid until
+ * zvdb_destroy -- the lifetime the reference gives result.point (test_hnsw.zig:67). NULL if
+ * id is out of range. Lets the Zig wrapper rebuild `[]const Node` from ids. */
+ZVDB_API const float *zvdb_get_point(const zvdb_index *ix, uint64_t id);
+
+/* Node.connections[layer] of node `id` (hnsw.zig:15): writes up to `cap` neighbour ids, returns
+ * the list length in *len (0 if the node has no such layer). */
+ZVDB_API int zvdb_get_connections(const zvdb_index *ix, uint64_t id, uint32_t layer, uint64_t *out,
+                                  uint32_t cap, uint32_t *len);
+
+/* Level of node `id` (= connections.len - 1, hnsw.zig:19), or -1 if there is no such node. */
+ZVDB_API int32_t zvdb_node_level(const zvdb_index *ix, uint64_t id);
+
+/* Flatten one layer into caller memory: adj[n x m] (0xFFFFFFFF padding) and deg[n] (may be NULL);
+ * nodes without that layer get degree 0. This is the table the device holds for layer 0. */
+ZVDB_API int zvdb_export_layer(const zvdb_index *ix, uint32_t layer, uint32_t *adj, uint32_t *deg);
+
+/* Replace the whole index by an externally built graph in CSR form (the search
+ * kernel takes "a graph as input"): points[n x dim], offsets[n+1], nbrs[offsets[n]], at most m
+ * neighbours per node, all ids < n. Only layer 0 is set; entry as given (the reference's is 0). */
+ZVDB_API int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim,
+                             const uint64_t *offsets, const uint32_t *nbrs, uint64_t entry);
+
+/* ---- search ------------------------------------------------------------------------------ */
+
+/* HNSW(T).search(query, k), hnsw.zig:194-236: best-first from the entry point over layer 0,
+ * exactly k pops, the popped set stable-sorted by distance. Writes min(k, reachable) results to
+ * ids/dist and that number to *count. An empty index gives *count = 0 and ZVDB_OK
+ * (test_hnsw.zig:43-53). Equivalent to zvdb_search_batch(nq = 1, ef = k). */
+ZVDB_API int zvdb_search(zvdb_index *ix, const float *query, uint32_t dim, uint32_t k, uint64_t *ids,
+                         float *dist, uint32_t *count);
+
+/* nq independent searches in one kernel launch: result row q = search(queries[q], ef)[0..k]
+ * (the reference has no ef parameter; its pop count IS the recall knob). ef >= k;
+ * ef = 0 means ef = k. HOST buffers: queries[nq x dim] in, ids[nq x k], dist[nq x k],
+ * counts[nq] out; unused slots hold ZVDB_INVALID_ID / 0. The host-device copies are part of
+ * the call. pops/evals (each may be NULL) receive the per-query number of heap pops and
+ * distance evaluations, the roofline numerators of SURVEY 8d. */
+ZVDB_API int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_t dim,
+                               uint32_t k, uint32_t ef, uint64_t *ids, float *dist, uint32_t *counts,
+                               uint32_t *pops, uint32_t *evals);
+
+/* Same search with DEVICE buffers, enqueued on `stream` (a cudaStream_t; NULL = the legacy
+ * default stream) without synchronising. Global ids are written as id * id_stride + id_base
+ * (1, 0 for a single index; G, rank for an id-sharded one). */
+ZVDB_API int zvdb_search_batch_device(zvdb_index *ix, const float *d_queries, uint64_t nq, uint32_t k,
+                                      uint32_t ef, uint64_t *d_ids, float *d_dist, uint32_t *d_counts,
+                                      uint32_t *d_pops, uint32_t *d_evals, uint64_t id_stride,
+                                      uint64_t id_base, void *stream);
+
+/* Push pending host-side inserts to the device now (otherwise done by the next search). */
+ZVDB_API int zvdb_sync_device(zvdb_index *ix);
+
+/* Launch shape override for tuning: warps cooperating on one query (0 = automatic). */
+ZVDB_API int zvdb_set_warps_per_query(zvdb_index *ix, uint32_t warps);
+
+/* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */
+ZVDB_API uint64_t zvdb_kernel_launches(const zvdb_index *ix);
+
+/* ---- shard merge --------------------------------------------------------------- */
+
+/* k-way merge of G per-shard result sets gathered as d_dist/d_ids [G][nq][k], d_counts [G][nq]
+ * (DEVICE buffers, e.g. the output of one all-gather), ordered by (distance, global id), into
+ * out_* [nq][k], out_counts[nq]. Enqueued on `stream`. No reference counterpart. */
+ZVDB_API int zvdb_merge_topk_device(const float *d_dist, const uint64_t *d_ids, const uint32_t *d_counts,
+                                    uint32_t G, uint64_t nq, uint32_t k, float *out_dist, uint64_t *out_ids,
+                                    uint32_t *out_counts, void *stream);
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+
+/* Message of the last failure on the calling thread ("" if none). Never NULL. */
+ZVDB_API const char *zvdb_last_error(void);
+
+/* Library / build identification, e.g. "zvdb_b200 0.1 sm_100a". */
+ZVDB_API const char *zvdb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZVDB_B200_H */

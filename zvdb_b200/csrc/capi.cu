@@ -1,0 +1,566 @@
+// capi.cu -- libzvdb_b200.so: the C ABI of include/zvdb_b200.h over the host graph (insert) and
+// the sm_100a kernels (search, scatter, merge). No CPU search path exists in this library.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/zvdb_b200.h"
+#include "host_graph.hpp"
+#include "search_kernel.cuh"
+
+namespace zvdb {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define ZV_CUDA(expr)                                                                            \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            cudaGetLastError();                                                                  \
+            return fail(e__ == cudaErrorMemoryAllocation ? ZVDB_ERR_OUT_OF_MEMORY : ZVDB_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+        }                                                                                        \
+    } while (0)
+
+// ---- K3: device copy of the flattened index -------------------------------------------------
+
+// Scatter re-sent layer-0 rows into the device table: rows[i][0..m) -> adj[ids[i]][0..m).
+__global__ void scatter_adj_rows_kernel(uint32_t *__restrict__ adj, const uint32_t *__restrict__ rows,
+                                        const uint32_t *__restrict__ ids, uint32_t count, uint32_t m) {
+    const uint64_t total = static_cast<uint64_t>(count) * m;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t r = static_cast<uint32_t>(i / m), c = static_cast<uint32_t>(i % m);
+        adj[static_cast<uint64_t>(ids[r]) * m + c] = rows[i];
+    }
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) cap = count;
+        return e;
+    }
+    void free_() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace zvdb
+
+using namespace zvdb;
+
+struct zvdb_index {
+    std::mutex mu;                  // the reference's global mutex, hnsw.zig:50
+    HostGraph g;
+    int device = 0;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;  // owned; used by the host-buffer entry points and uploads
+    float *d_arena = nullptr;       // [cap_rows][row_floats]
+    uint32_t *d_adj = nullptr;      // [cap_rows][m]
+    uint64_t cap_rows = 0, n_dev = 0;
+    DevBuf<float> q_buf, dist_buf;
+    DevBuf<uint64_t> ids_buf;
+    DevBuf<uint32_t> cnt_buf, pops_buf, evals_buf, scat_rows, scat_ids;
+    uint32_t warps_per_query = 0;
+    std::atomic<uint64_t> launches{0};
+};
+
+namespace zvdb {
+
+static int ensure_capacity(zvdb_index *ix, uint64_t rows) {
+    if (rows <= ix->cap_rows) return ZVDB_OK;
+    uint64_t nc = std::max<uint64_t>(rows, std::max<uint64_t>(ix->cap_rows * 2, 1024));
+    float *na = nullptr; uint32_t *nj = nullptr;
+    const HostGraph &g = ix->g;
+    ZV_CUDA(cudaMalloc(&na, nc * g.row_floats * sizeof(float)));
+    cudaError_t e = cudaMalloc(&nj, nc * g.m * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(na); ZV_CUDA(e); }
+    if (ix->n_dev) {
+        ZV_CUDA(cudaMemcpyAsync(na, ix->d_arena, ix->n_dev * g.row_floats * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        ZV_CUDA(cudaMemcpyAsync(nj, ix->d_adj, ix->n_dev * g.m * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ix->stream));
+        ZV_CUDA(cudaStreamSynchronize(ix->stream));
+    }
+    cudaFree(ix->d_arena); cudaFree(ix->d_adj);
+    ix->d_arena = na; ix->d_adj = nj; ix->cap_rows = nc;
+    return ZVDB_OK;
+}
+
+// Bring the device copy up to date with the host graph: new arena rows are appended, layer-0 rows
+// that changed are scattered (or the whole table re-sent when most of it changed).
+static int sync_device_locked(zvdb_index *ix) {
+    HostGraph &g = ix->g;
+    if (g.n == 0) return ZVDB_OK;
+    if (g.rows_uploaded == g.n && !g.adj_all_dirty && g.dirty.empty()) return ZVDB_OK;
+    ZV_CUDA(cudaSetDevice(ix->device));
+    int rc = ensure_capacity(ix, g.n);
+    if (rc) return rc;
+    for (uint64_t r = g.rows_uploaded; r < g.n;) {
+        const uint64_t chunk = r / g.rows_per_chunk;
+        const uint64_t end = std::min<uint64_t>(g.n, (chunk + 1) * g.rows_per_chunk);
+        ZV_CUDA(cudaMemcpyAsync(ix->d_arena + r * g.row_floats, g.point(r), (end - r) * g.row_floats * sizeof(float),
+                                cudaMemcpyHostToDevice, ix->stream));
+        r = end;
+    }
+    if (g.adj_all_dirty || g.dirty.size() * 8 > g.n) {
+        ZV_CUDA(cudaMemcpyAsync(ix->d_adj, g.adj0.data(), g.n * g.m * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+    } else if (!g.dirty.empty()) {
+        std::sort(g.dirty.begin(), g.dirty.end());
+        g.dirty.erase(std::unique(g.dirty.begin(), g.dirty.end()), g.dirty.end());
+        const size_t cnt = g.dirty.size();
+        std::vector<uint32_t> rows(cnt * g.m);
+        for (size_t i = 0; i < cnt; ++i)
+            std::memcpy(rows.data() + i * g.m, g.adj0.data() + static_cast<size_t>(g.dirty[i]) * g.m, g.m * sizeof(uint32_t));
+        ZV_CUDA(ix->scat_rows.reserve(cnt * g.m));
+        ZV_CUDA(ix->scat_ids.reserve(cnt));
+        ZV_CUDA(cudaMemcpyAsync(ix->scat_rows.p, rows.data(), cnt * g.m * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+        ZV_CUDA(cudaMemcpyAsync(ix->scat_ids.p, g.dirty.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+        const uint64_t total = cnt * g.m;
+        const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((total + 255) / 256, 148ull * 8));
+        scatter_adj_rows_kernel<<<blocks, 256, 0, ix->stream>>>(ix->d_adj, ix->scat_rows.p, ix->scat_ids.p,
+                                                                static_cast<uint32_t>(cnt), g.m);
+        ix->launches++;
+        ZV_CUDA(cudaGetLastError());
+        ZV_CUDA(cudaStreamSynchronize(ix->stream));   // `rows` is stack-owned pageable memory
+    }
+    ZV_CUDA(cudaStreamSynchronize(ix->stream));
+    g.rows_uploaded = g.n; g.dirty.clear(); g.adj_all_dirty = false;
+    ix->n_dev = g.n;
+    return ZVDB_OK;
+}
+
+// ---- K1 launch ------------------------------------------------------------------------------
+
+template <int CPL, int METRIC>
+static cudaError_t launch_search_inst(const SearchParams &p, unsigned threads, size_t smem, cudaStream_t s) {
+    auto kern = search_layer0_kernel<CPL, METRIC>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<p.nq, threads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int METRIC>
+static cudaError_t launch_search_metric(int cpl, const SearchParams &p, unsigned threads, size_t smem, cudaStream_t s) {
+    switch (cpl) {
+        case 1: return launch_search_inst<1, METRIC>(p, threads, smem, s);
+        case 2: return launch_search_inst<2, METRIC>(p, threads, smem, s);
+        case 4: return launch_search_inst<4, METRIC>(p, threads, smem, s);
+        case 6: return launch_search_inst<6, METRIC>(p, threads, smem, s);
+        case 8: return launch_search_inst<8, METRIC>(p, threads, smem, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// Device buffers in, device buffers out, no synchronisation. Caller holds the lock and has synced
+// the device copy.
+static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t *d_ids,
+                         float *d_dist, uint32_t *d_counts, uint32_t *d_pops, uint32_t *d_evals, uint64_t id_stride,
+                         uint64_t id_base, cudaStream_t s) {
+    const HostGraph &g = ix->g;
+    if (nq == 0) return ZVDB_OK;
+    if (nq > 0x7FFFFFFFull) return fail(ZVDB_ERR_UNSUPPORTED, "nq exceeds 2^31-1 queries per launch");
+    SearchParams p{};
+    p.arena = reinterpret_cast<const float4 *>(ix->d_arena);
+    p.adj = ix->d_adj;
+    p.queries = d_q;
+    p.ids = d_ids; p.dist = d_dist; p.counts = d_counts; p.pops = d_pops; p.evals = d_evals;
+    p.id_stride = id_stride; p.id_base = id_base;
+    p.row_chunks = g.row_floats / 4;
+    p.m = g.m; p.n = static_cast<uint32_t>(g.n); p.entry = static_cast<uint32_t>(g.entry); p.dim = g.dim;
+    p.nq = static_cast<uint32_t>(nq); p.k = k; p.ef = ef;
+    const uint64_t bound = std::min<uint64_t>(g.n, 1ull + static_cast<uint64_t>(ef) * g.m);   // visited-set maximum
+    const uint64_t slots = bound + bound / 3 + 16;
+    const uint64_t hash_words = std::max<uint64_t>(slots, 2ull * next_pow2(ef));
+    const uint64_t smem = static_cast<uint64_t>(ef) * 8 + 32 * 8 + hash_words * 4 + 32 * 4 + 32 * 4 + 16;
+    if (smem > ix->smem_optin) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "search needs %llu bytes of shared memory per query (ef=%u, m=%u); this device allows %zu. Lower ef.",
+                 static_cast<unsigned long long>(smem), ef, g.m, ix->smem_optin);
+        return fail(ZVDB_ERR_UNSUPPORTED, buf);
+    }
+    p.slots = static_cast<uint32_t>(slots); p.hash_words = static_cast<uint32_t>(hash_words);
+    const uint32_t chunks_per_lane = (p.row_chunks + 31) / 32;
+    int cpl = chunks_per_lane <= 1 ? 1 : chunks_per_lane <= 2 ? 2 : chunks_per_lane <= 4 ? 4 : chunks_per_lane <= 6 ? 6 : 8;
+    if (chunks_per_lane > 8) return fail(ZVDB_ERR_UNSUPPORTED, "dim > 1024 is not built into the search kernel");
+    // Team width: enough warps per SM to cover HBM latency even when shared memory limits the CTAs per SM.
+    uint32_t W = ix->warps_per_query;
+    if (W == 0) {
+        const uint64_t ctas_per_sm = std::min<uint64_t>(32, (227ull * 1024) / (smem + 1024));
+        W = 1;
+        while (W < 8 && ctas_per_sm * W < 32) W *= 2;
+    }
+    W = std::min<uint32_t>(std::max<uint32_t>(W, 1), 8);
+    cudaError_t e;
+    switch (g.metric) {
+        case 0: e = launch_search_metric<kMetricL2>(cpl, p, W * 32, smem, s); break;
+        case 1: e = launch_search_metric<kMetricCos>(cpl, p, W * 32, smem, s); break;
+        default: e = launch_search_metric<kMetricDot>(cpl, p, W * 32, smem, s); break;
+    }
+    ix->launches++;
+    ZV_CUDA(e);
+    return ZVDB_OK;
+}
+
+// ---- K5: shard merge ------------------------------------------------------------------------
+
+struct MergeLess {
+    const uint64_t *gid;   // shared-memory copy of the candidates' global ids
+    __device__ __forceinline__ bool operator()(uint64_t x, uint64_t y) const {
+        const uint32_t dx = static_cast<uint32_t>(x >> 32), dy = static_cast<uint32_t>(y >> 32);
+        if (dx != dy) return dx < dy;
+        const uint32_t ix_ = static_cast<uint32_t>(x), iy = static_cast<uint32_t>(y);
+        if (ix_ == kInvalidId || iy == kInvalidId) return ix_ != kInvalidId && iy == kInvalidId;
+        return gid[ix_] < gid[iy];
+    }
+};
+
+// One CTA per query: gather the G shard lists into shared memory, bitonic-sort them by
+// (distance, global id), write the first k.
+__global__ void merge_topk_kernel(const float *__restrict__ d_dist, const uint64_t *__restrict__ d_ids,
+                                  const uint32_t *__restrict__ d_counts, uint32_t G, uint32_t nq, uint32_t k,
+                                  float *__restrict__ out_dist, uint64_t *__restrict__ out_ids,
+                                  uint32_t *__restrict__ out_counts, uint32_t p2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);   // [p2]  ordered(dist) << 32 | slot
+    uint64_t *gid = keys + p2;                                 // [G*k]
+    const uint32_t q = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const uint32_t total = G * k;
+    for (uint32_t i = tid; i < p2; i += T) {
+        uint64_t key = ~0ull;
+        if (i < total) {
+            const uint32_t gsh = i / k, j = i % k;
+            const size_t src = (static_cast<size_t>(gsh) * nq + q) * k + j;
+            gid[i] = d_ids[src];
+            if (j < d_counts[static_cast<size_t>(gsh) * nq + q]) key = (static_cast<uint64_t>(float_to_ordered(d_dist[src])) << 32) | i;
+        }
+        keys[i] = key;
+    }
+    bitonic_sort_u64(keys, p2, MergeLess{gid});
+    uint32_t valid = 0;
+    for (uint32_t gsh = 0; gsh < G; ++gsh) valid += min(d_counts[static_cast<size_t>(gsh) * nq + q], k);
+    const uint32_t nres = min(valid, k);
+    for (uint32_t r = tid; r < k; r += T) {
+        const size_t o = static_cast<size_t>(q) * k + r;
+        if (r < nres) {
+            const uint64_t key = keys[r];
+            out_ids[o] = gid[static_cast<uint32_t>(key)];
+            out_dist[o] = ordered_to_float(static_cast<uint32_t>(key >> 32));
+        } else {
+            out_ids[o] = ~0ull;
+            out_dist[o] = 0.0f;
+        }
+    }
+    if (tid == 0) out_counts[q] = nres;
+}
+
+}  // namespace zvdb
+
+// ================================ exported C ABI ================================================
+
+extern "C" {
+
+const char *zvdb_last_error(void) { return g_last_error.c_str(); }
+const char *zvdb_version(void) { return "zvdb_b200 0.1 sm_100a"; }
+
+int zvdb_create(zvdb_index **out, uint32_t dim, uint32_t m, uint32_t ef_construction, int metric, int device) {
+    if (!out) return fail(ZVDB_ERR_INVALID, "zvdb_create: out is null");
+    *out = nullptr;
+    if (m == 0) return fail(ZVDB_ERR_INVALID, "zvdb_create: m must be >= 1");
+    if (metric < 0 || metric > 2) return fail(ZVDB_ERR_INVALID, "zvdb_create: unknown metric");
+    if (dim > 1024) return fail(ZVDB_ERR_UNSUPPORTED, "zvdb_create: dim > 1024 is not built into the search kernel");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return fail(ZVDB_ERR_CUDA, std::string("zvdb_create: no usable CUDA device (there is no CPU fallback): ") +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range"));
+    }
+    cudaDeviceProp prop{};
+    ZV_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ZVDB_ERR_CUDA, std::string("zvdb_create: device '") + prop.name + "' is not sm_100; this library carries sm_100a code only");
+    zvdb_index *ix = new (std::nothrow) zvdb_index();
+    if (!ix) return fail(ZVDB_ERR_OUT_OF_MEMORY, "zvdb_create: out of memory");
+    ix->device = device;
+    ix->num_sms = prop.multiProcessorCount;
+    ix->smem_optin = prop.sharedMemPerBlockOptin;
+    ix->g.m = m; ix->g.ef_construction = ef_construction; ix->g.metric = metric;
+    if (dim) ix->g.fix_dim(dim);
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ix; ZV_CUDA(e); }
+    *out = ix;
+    return ZVDB_OK;
+}
+
+void zvdb_destroy(zvdb_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) { cudaStreamSynchronize(ix->stream); cudaStreamDestroy(ix->stream); }
+    cudaFree(ix->d_arena); cudaFree(ix->d_adj);
+    ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
+    ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_();
+    delete ix;
+}
+
+int zvdb_set_level_seed(zvdb_index *ix, uint64_t seed) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->g.rng = seed * 0x9E3779B97F4A7C15ull + 0x243F6A8885A308D3ull;
+    return ZVDB_OK;
+}
+
+static int insert_locked(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, const int32_t *levels) {
+    HostGraph &g = ix->g;
+    if (n == 0) return ZVDB_OK;
+    if (!points) return fail(ZVDB_ERR_INVALID, "insert: null point");
+    if (g.dim == 0) {
+        if (dim == 0) return fail(ZVDB_ERR_INVALID, "insert: dim must be >= 1");
+        if (dim > 1024) return fail(ZVDB_ERR_UNSUPPORTED, "insert: dim > 1024 is not built into the search kernel");
+        g.fix_dim(dim);   // the reference's dim is implied by the first point
+    }
+    if (dim != g.dim) return fail(ZVDB_ERR_DIM_MISMATCH, "Mismatched dimensions in distance calculation");
+    cudaSetDevice(ix->device);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (g.insert(points + i * static_cast<uint64_t>(dim), levels ? levels[i] : -1))
+            return fail(ZVDB_ERR_OUT_OF_MEMORY, "insert: out of memory");
+    }
+    return ZVDB_OK;
+}
+
+int zvdb_insert(zvdb_index *ix, const float *point, uint32_t dim) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lk(ix->mu);   // hnsw.zig:74-75
+    return insert_locked(ix, point, 1, dim, nullptr);
+}
+
+int zvdb_insert_batch(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, const int32_t *levels) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return insert_locked(ix, points, n, dim, levels);
+}
+
+uint64_t zvdb_count(const zvdb_index *ix) { return ix ? ix->g.n : 0; }
+uint32_t zvdb_dim(const zvdb_index *ix) { return ix ? ix->g.dim : 0; }
+uint32_t zvdb_max_level(const zvdb_index *ix) { return ix ? ix->g.max_level : 0; }
+int64_t zvdb_entry_point(const zvdb_index *ix) { return (ix && ix->g.has_entry) ? static_cast<int64_t>(ix->g.entry) : -1; }
+
+const float *zvdb_get_point(const zvdb_index *ix, uint64_t id) {
+    if (!ix || id >= ix->g.n) return nullptr;
+    return ix->g.point(id);
+}
+
+int zvdb_get_connections(const zvdb_index *cix, uint64_t id, uint32_t layer, uint64_t *out, uint32_t cap, uint32_t *len) {
+    if (!cix || !len) return fail(ZVDB_ERR_INVALID, "null argument");
+    zvdb_index *ix = const_cast<zvdb_index *>(cix);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    HostGraph &g = ix->g;
+    if (id >= g.n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "NodeNotFound");
+    *len = 0;
+    if (layer > g.level[id]) return ZVDB_OK;
+    const uint32_t l = g.list_len(id, layer);
+    const uint32_t *list = g.list_ptr(id, layer);
+    *len = l;
+    for (uint32_t i = 0; i < l && i < cap && out; ++i) out[i] = list[i];
+    return ZVDB_OK;
+}
+
+int32_t zvdb_node_level(const zvdb_index *ix, uint64_t id) {
+    if (!ix || id >= ix->g.n) return -1;
+    return ix->g.level[id];
+}
+
+int zvdb_export_layer(const zvdb_index *cix, uint32_t layer, uint32_t *adj, uint32_t *deg) {
+    if (!cix || !adj) return fail(ZVDB_ERR_INVALID, "null argument");
+    zvdb_index *ix = const_cast<zvdb_index *>(cix);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    HostGraph &g = ix->g;
+    for (uint64_t i = 0; i < g.n; ++i) {
+        uint32_t l = 0;
+        if (layer <= g.level[i]) {
+            l = g.list_len(i, layer);
+            std::memcpy(adj + i * g.m, g.list_ptr(i, layer), l * sizeof(uint32_t));
+        }
+        for (uint32_t t = l; t < g.m; ++t) adj[i * g.m + t] = kInvalidId;
+        if (deg) deg[i] = l;
+    }
+    return ZVDB_OK;
+}
+
+int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, const uint64_t *offsets,
+                    const uint32_t *nbrs, uint64_t entry) {
+    if (!ix || (n && (!points || !offsets))) return fail(ZVDB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    HostGraph &g = ix->g;
+    if (dim == 0 || dim > 1024) return fail(ZVDB_ERR_UNSUPPORTED, "load_graph: dim must be in 1..1024");
+    if (g.dim != 0 && g.dim != dim && g.n != 0) return fail(ZVDB_ERR_DIM_MISMATCH, "Mismatched dimensions in distance calculation");
+    if (n >= 0xFFFFFFFEull) return fail(ZVDB_ERR_UNSUPPORTED, "load_graph: more than 2^32-2 nodes in one shard");
+    if (n && entry >= n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "load_graph: entry out of range");
+    for (uint64_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > g.m)
+            return fail(ZVDB_ERR_INVALID, "load_graph: a node has more than m neighbours (or offsets decrease)");
+    }
+    for (uint64_t e = 0; n && e < offsets[n]; ++e)
+        if (nbrs[e] >= n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "load_graph: neighbour id out of range");
+    cudaSetDevice(ix->device);
+    g.reset_nodes();
+    g.fix_dim(dim);
+    try {
+        g.adj0.assign(n * g.m, kInvalidId);
+        g.level.assign(n, 0);
+        g.upper_off.assign(n, ~0ull);
+    } catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "load_graph: out of memory"); }
+    const uint64_t nchunks = (n + g.rows_per_chunk - 1) / g.rows_per_chunk;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        float *p = nullptr;
+        ZV_CUDA(cudaHostAlloc(&p, static_cast<size_t>(g.rows_per_chunk) * g.row_floats * sizeof(float), cudaHostAllocDefault));
+        g.chunks.push_back(p);
+    }
+    g.n = n;
+    for (uint64_t i = 0; i < n; ++i) {
+        float *row = g.point_mut(i);
+        std::memcpy(row, points + i * dim, dim * sizeof(float));
+        if (g.metric == 1) {
+            double s = 0.0;
+            for (uint32_t t = 0; t < dim; ++t) s += static_cast<double>(row[t]) * static_cast<double>(row[t]);
+            if (s > 0.0) {
+                const double inv = 1.0 / std::sqrt(s);
+                for (uint32_t t = 0; t < dim; ++t) row[t] = static_cast<float>(static_cast<double>(row[t]) * inv);
+            }
+        }
+        for (uint32_t t = dim; t < g.row_floats; ++t) row[t] = 0.0f;
+        const uint64_t b = offsets[i], e = offsets[i + 1];
+        for (uint64_t t = b; t < e; ++t) g.adj0[i * g.m + (t - b)] = nbrs[t];
+    }
+    g.has_entry = n > 0; g.entry = entry; g.max_level = 0;
+    g.rows_uploaded = 0; g.adj_all_dirty = true;
+    ix->n_dev = 0;
+    return ZVDB_OK;
+}
+
+int zvdb_sync_device(zvdb_index *ix) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return sync_device_locked(ix);
+}
+
+int zvdb_set_warps_per_query(zvdb_index *ix, uint32_t warps) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    if (warps > 8 || (warps & (warps - 1))) return fail(ZVDB_ERR_INVALID, "warps per query must be 0, 1, 2, 4 or 8");
+    ix->warps_per_query = warps;
+    return ZVDB_OK;
+}
+
+uint64_t zvdb_kernel_launches(const zvdb_index *ix) { return ix ? ix->launches.load() : 0; }
+
+int zvdb_search_batch_device(zvdb_index *ix, const float *d_queries, uint64_t nq, uint32_t k, uint32_t ef,
+                             uint64_t *d_ids, float *d_dist, uint32_t *d_counts, uint32_t *d_pops, uint32_t *d_evals,
+                             uint64_t id_stride, uint64_t id_base, void *stream) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    if (nq == 0) return ZVDB_OK;
+    if (!d_queries || !d_ids || !d_dist || !d_counts) return fail(ZVDB_ERR_INVALID, "search: null buffer");
+    if (k == 0) return fail(ZVDB_ERR_INVALID, "search: k must be >= 1");
+    if (ef == 0) ef = k;
+    if (ef < k) return fail(ZVDB_ERR_INVALID, "search: ef must be >= k");
+    std::lock_guard<std::mutex> lk(ix->mu);   // hnsw.zig:195-196
+    ZV_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ix->g.n == 0 || !ix->g.has_entry) {   // empty index: empty result, not an error (test_hnsw.zig:43-53)
+        ZV_CUDA(cudaMemsetAsync(d_counts, 0, nq * sizeof(uint32_t), s));
+        ZV_CUDA(cudaMemsetAsync(d_ids, 0xFF, nq * k * sizeof(uint64_t), s));
+        ZV_CUDA(cudaMemsetAsync(d_dist, 0, nq * k * sizeof(float), s));
+        if (d_pops) ZV_CUDA(cudaMemsetAsync(d_pops, 0, nq * sizeof(uint32_t), s));
+        if (d_evals) ZV_CUDA(cudaMemsetAsync(d_evals, 0, nq * sizeof(uint32_t), s));
+        return ZVDB_OK;
+    }
+    int rc = sync_device_locked(ix);
+    if (rc) return rc;
+    return launch_search(ix, d_queries, nq, k, ef, d_ids, d_dist, d_counts, d_pops, d_evals, id_stride, id_base, s);
+}
+
+int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t ef,
+                      uint64_t *ids, float *dist, uint32_t *counts, uint32_t *pops, uint32_t *evals) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    if (nq == 0) return ZVDB_OK;
+    if (!queries || !ids || !dist || !counts) return fail(ZVDB_ERR_INVALID, "search: null buffer");
+    if (k == 0) return fail(ZVDB_ERR_INVALID, "search: k must be >= 1");
+    if (ef == 0) ef = k;
+    if (ef < k) return fail(ZVDB_ERR_INVALID, "search: ef must be >= k");
+    std::lock_guard<std::mutex> lk(ix->mu);   // hnsw.zig:195-196
+    ZV_CUDA(cudaSetDevice(ix->device));       // no device, no search: there is no CPU path
+    if (ix->g.n == 0 || !ix->g.has_entry) {
+        for (uint64_t i = 0; i < nq; ++i) counts[i] = 0;
+        for (uint64_t i = 0; i < nq * k; ++i) { ids[i] = ZVDB_INVALID_ID; dist[i] = 0.0f; }
+        if (pops) for (uint64_t i = 0; i < nq; ++i) pops[i] = 0;
+        if (evals) for (uint64_t i = 0; i < nq; ++i) evals[i] = 0;
+        return ZVDB_OK;
+    }
+    if (dim != ix->g.dim) return fail(ZVDB_ERR_DIM_MISMATCH, "Mismatched dimensions in distance calculation");
+    int rc = sync_device_locked(ix);
+    if (rc) return rc;
+    ZV_CUDA(ix->q_buf.reserve(nq * dim));
+    ZV_CUDA(ix->ids_buf.reserve(nq * k));
+    ZV_CUDA(ix->dist_buf.reserve(nq * k));
+    ZV_CUDA(ix->cnt_buf.reserve(nq));
+    if (pops) ZV_CUDA(ix->pops_buf.reserve(nq));
+    if (evals) ZV_CUDA(ix->evals_buf.reserve(nq));
+    cudaStream_t s = ix->stream;
+    ZV_CUDA(cudaMemcpyAsync(ix->q_buf.p, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = launch_search(ix, ix->q_buf.p, nq, k, ef, ix->ids_buf.p, ix->dist_buf.p, ix->cnt_buf.p,
+                       pops ? ix->pops_buf.p : nullptr, evals ? ix->evals_buf.p : nullptr, 1, 0, s);
+    if (rc) return rc;
+    ZV_CUDA(cudaMemcpyAsync(ids, ix->ids_buf.p, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    ZV_CUDA(cudaMemcpyAsync(dist, ix->dist_buf.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    ZV_CUDA(cudaMemcpyAsync(counts, ix->cnt_buf.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (pops) ZV_CUDA(cudaMemcpyAsync(pops, ix->pops_buf.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (evals) ZV_CUDA(cudaMemcpyAsync(evals, ix->evals_buf.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ZV_CUDA(cudaStreamSynchronize(s));
+    return ZVDB_OK;
+}
+
+int zvdb_search(zvdb_index *ix, const float *query, uint32_t dim, uint32_t k, uint64_t *ids, float *dist, uint32_t *count) {
+    if (k == 0) {   // search(query, 0): zero pops, empty slice
+        if (count) *count = 0;
+        return ix ? ZVDB_OK : fail(ZVDB_ERR_INVALID, "null index");
+    }
+    return zvdb_search_batch(ix, query, 1, dim, k, k, ids, dist, count, nullptr, nullptr);
+}
+
+int zvdb_merge_topk_device(const float *d_dist, const uint64_t *d_ids, const uint32_t *d_counts, uint32_t G,
+                           uint64_t nq, uint32_t k, float *out_dist, uint64_t *out_ids, uint32_t *out_counts,
+                           void *stream) {
+    if (!d_dist || !d_ids || !d_counts || !out_dist || !out_ids || !out_counts) return fail(ZVDB_ERR_INVALID, "merge: null buffer");
+    if (G == 0 || k == 0) return fail(ZVDB_ERR_INVALID, "merge: G and k must be >= 1");
+    if (nq == 0) return ZVDB_OK;
+    const uint64_t total = static_cast<uint64_t>(G) * k;
+    if (total > 4096) return fail(ZVDB_ERR_UNSUPPORTED, "merge: G*k > 4096");
+    const uint32_t p2 = next_pow2(static_cast<uint32_t>(total));
+    const size_t smem = static_cast<size_t>(p2) * 8 + total * 8;
+    const unsigned threads = p2 >= 512 ? 256 : (p2 >= 128 ? 64 : 32);
+    if (smem > 48 * 1024)
+        ZV_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    merge_topk_kernel<<<static_cast<unsigned>(nq), threads, smem, static_cast<cudaStream_t>(stream)>>>(
+        d_dist, d_ids, d_counts, G, static_cast<uint32_t>(nq), k, out_dist, out_ids, out_counts, p2);
+    ZV_CUDA(cudaGetLastError());
+    return ZVDB_OK;
+}
+
+}  // extern "C"

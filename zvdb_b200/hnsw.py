@@ -1,0 +1,231 @@
+"""Host-side mirror of the reference's public type `HNSW(T)` (src/hnsw.zig:8, re-exported by
+src/zvdb.zig:1) over the C ABI of libzvdb_b200.so.
+
+Same names, argument meaning and error behaviour as the reference, so tests read like
+src/test_hnsw.zig:
+
+    hnsw = HNSW(m=16, ef_construction=200)        # HNSW(f32).init(allocator, 16, 200)
+    hnsw.insert([1, 2, 3])                        # try hnsw.insert(&[_]f32{1,2,3})
+    results = hnsw.search([3, 4, 5], 2)           # try hnsw.search(query, 2) -> []const Node
+    results[0].point, len(results)                # .point, .len
+    hnsw.nodes.count()                            # hnsw.nodes.count()  (test_hnsw.zig:198)
+    hnsw.deinit()
+
+All searching happens in the CUDA kernels of the library; nothing here computes a distance.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass
+class Node:
+    """One search result: the fields of the reference's `Node` a caller can read (hnsw.zig:12-16)."""
+    id: int
+    point: np.ndarray          # view of the index's own copy, valid until deinit (hnsw.zig:24-26)
+    distance: float            # squared L2 to the query (the reference recomputes it; we return it)
+    _owner: "HNSW"
+
+    @property
+    def connections(self):
+        """connections[layer] lists, hnsw.zig:15."""
+        out = []
+        layer = 0
+        while True:
+            lst = self._owner.connections(self.id, layer)
+            if lst is None:
+                break
+            out.append(lst)
+            layer += 1
+        return out
+
+
+class _Nodes:
+    def __init__(self, owner: "HNSW"):
+        self._o = owner
+
+    def count(self) -> int:
+        return self._o.count()
+
+
+class HNSW:
+    """`HNSW(f32)`: init / deinit / insert / search, plus the batched entry points of the C ABI."""
+
+    def __init__(self, m: int = 16, ef_construction: int = 200, *, dim: int = 0, metric: int = L.METRIC_L2,
+                 device: int = 0, level_seed: Optional[int] = None):
+        self._h = C.c_void_p()
+        self.m = m
+        self.ef_construction = ef_construction
+        self.metric = metric
+        self.device = device
+        L.check(L.lib().zvdb_create(C.byref(self._h), dim, m, ef_construction, metric, device))
+        if level_seed is not None:
+            L.check(L.lib().zvdb_set_level_seed(self._h, level_seed))
+        self.nodes = _Nodes(self)
+
+    # -- lifecycle --------------------------------------------------------------------------
+    def deinit(self) -> None:
+        if self._h:
+            L.lib().zvdb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.deinit()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.deinit()
+
+    # -- state the reference exposes -----------------------------------------------------------
+    def count(self) -> int:
+        return int(L.lib().zvdb_count(self._h))
+
+    @property
+    def dim(self) -> int:
+        return int(L.lib().zvdb_dim(self._h))
+
+    @property
+    def max_level(self) -> int:
+        return int(L.lib().zvdb_max_level(self._h))
+
+    @property
+    def entry_point(self) -> Optional[int]:
+        e = int(L.lib().zvdb_entry_point(self._h))
+        return None if e < 0 else e
+
+    def point(self, node_id: int) -> np.ndarray:
+        p = L.lib().zvdb_get_point(self._h, node_id)
+        if not p:
+            raise L.ZvdbError(L.ERR_NODE_NOT_FOUND, "NodeNotFound")
+        return np.ctypeslib.as_array(p, shape=(self.dim,))
+
+    def node_level(self, node_id: int) -> int:
+        return int(L.lib().zvdb_node_level(self._h, node_id))
+
+    def connections(self, node_id: int, layer: int = 0) -> Optional[list]:
+        """Neighbour ids of `node_id` on `layer`; None if the node has no such layer."""
+        lv = self.node_level(node_id)
+        if lv < 0:
+            raise L.ZvdbError(L.ERR_NODE_NOT_FOUND, "NodeNotFound")
+        if layer > lv:
+            return None
+        buf = (C.c_uint64 * max(self.m, 1))()
+        n = C.c_uint32(0)
+        L.check(L.lib().zvdb_get_connections(self._h, node_id, layer, buf, self.m, C.byref(n)))
+        return [int(buf[i]) for i in range(n.value)]
+
+    def export_layer(self, layer: int = 0):
+        """Padded adjacency [n, m] (0xFFFFFFFF padding) and degrees [n] of one layer."""
+        n = self.count()
+        adj = np.full((max(n, 1), self.m), 0xFFFFFFFF, np.uint32)
+        deg = np.zeros(max(n, 1), np.uint32)
+        L.check(L.lib().zvdb_export_layer(self._h, layer, adj.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                          deg.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return adj[:n], deg[:n]
+
+    # -- insert (hnsw.zig:73) --------------------------------------------------------------------
+    def insert(self, point: Sequence[float]) -> None:
+        p = np.ascontiguousarray(point, np.float32).reshape(-1)
+        L.check(L.lib().zvdb_insert(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.size))
+
+    def insert_batch(self, points, levels=None) -> None:
+        p = np.ascontiguousarray(points, np.float32)
+        if p.ndim != 2:
+            raise ValueError("points must be [n, dim]")
+        lv = None
+        if levels is not None:
+            lv = np.ascontiguousarray(levels, np.int32)
+        L.check(L.lib().zvdb_insert_batch(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.shape[0], p.shape[1],
+                                          lv.ctypes.data_as(C.POINTER(C.c_int32)) if lv is not None else None))
+
+    def load_graph(self, points, offsets, nbrs, entry: int = 0) -> None:
+        """Replace the index by an external graph in CSR form (layer 0 only)."""
+        p = np.ascontiguousarray(points, np.float32)
+        off = np.ascontiguousarray(offsets, np.uint64)
+        nb = np.ascontiguousarray(nbrs, np.uint32)
+        L.check(L.lib().zvdb_load_graph(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.shape[0], p.shape[1],
+                                        off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        nb.ctypes.data_as(C.POINTER(C.c_uint32)), entry))
+
+    def load_padded_graph(self, points, adj, entry: int = 0) -> None:
+        """Same, from a padded table adj[n, <=m] with 0xFFFFFFFF padding."""
+        adj = np.ascontiguousarray(adj, np.uint32)
+        valid = adj != 0xFFFFFFFF
+        deg = valid.sum(axis=1).astype(np.uint64)
+        off = np.zeros(adj.shape[0] + 1, np.uint64)
+        np.cumsum(deg, out=off[1:])
+        self.load_graph(points, off, adj[valid], entry)
+
+    # -- search (hnsw.zig:194) -------------------------------------------------------------------
+    def search(self, query: Sequence[float], k: int) -> list:
+        """`search(query, k)`: list of Node, len = min(k, reachable); empty index -> []."""
+        q = np.ascontiguousarray(query, np.float32).reshape(-1)
+        if k == 0:
+            return []
+        ids = np.empty(k, np.uint64)
+        dist = np.empty(k, np.float32)
+        cnt = C.c_uint32(0)
+        L.check(L.lib().zvdb_search(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, k,
+                                    ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                    dist.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt)))
+        return [Node(int(ids[i]), self.point(int(ids[i])), float(dist[i]), self) for i in range(cnt.value)]
+
+    def search_batch(self, queries, k: int, ef: int = 0, counters: bool = False):
+        """Rows q: search(queries[q], ef)[0..k]. Host arrays in, host arrays out (copies are inside).
+
+        Returns (ids[nq,k] u64, dist[nq,k] f32, counts[nq] u32[, pops[nq], evals[nq]])."""
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        nq, dim = q.shape
+        ids = np.empty((nq, k), np.uint64)
+        dist = np.empty((nq, k), np.float32)
+        counts = np.empty(nq, np.uint32)
+        pops = np.empty(nq, np.uint32) if counters else None
+        evals = np.empty(nq, np.uint32) if counters else None
+        L.check(L.lib().zvdb_search_batch(self._h, q.ctypes.data, nq, dim, k, ef, ids.ctypes.data, dist.ctypes.data,
+                                          counts.ctypes.data, pops.ctypes.data if counters else None,
+                                          evals.ctypes.data if counters else None))
+        if counters:
+            return ids, dist, counts, pops, evals
+        return ids, dist, counts
+
+    def search_batch_ptr(self, q_ptr: int, nq: int, dim: int, k: int, ef: int, ids_ptr: int, dist_ptr: int,
+                         counts_ptr: int, pops_ptr: int = 0, evals_ptr: int = 0) -> None:
+        """zvdb_search_batch on raw HOST addresses (e.g. pinned torch tensors' data_ptr())."""
+        L.check(L.lib().zvdb_search_batch(self._h, q_ptr, nq, dim, k, ef, ids_ptr, dist_ptr, counts_ptr,
+                                          pops_ptr or None, evals_ptr or None))
+
+    def search_batch_device(self, d_queries: int, nq: int, k: int, ef: int, d_ids: int, d_dist: int, d_counts: int,
+                            d_pops: int = 0, d_evals: int = 0, id_stride: int = 1, id_base: int = 0,
+                            stream: int = 0) -> None:
+        """zvdb_search_batch_device on raw DEVICE addresses; enqueued on `stream`, not synchronised."""
+        L.check(L.lib().zvdb_search_batch_device(self._h, d_queries, nq, k, ef, d_ids, d_dist, d_counts,
+                                                 d_pops or None, d_evals or None, id_stride, id_base, stream or None))
+
+    def sync_device(self) -> None:
+        L.check(L.lib().zvdb_sync_device(self._h))
+
+    def set_warps_per_query(self, warps: int) -> None:
+        L.check(L.lib().zvdb_set_warps_per_query(self._h, warps))
+
+    def kernel_launches(self) -> int:
+        return int(L.lib().zvdb_kernel_launches(self._h))
+
+
+def merge_topk_device(d_dist: int, d_ids: int, d_counts: int, G: int, nq: int, k: int, out_dist: int, out_ids: int,
+                      out_counts: int, stream: int = 0) -> None:
+    """zvdb_merge_topk_device on raw device addresses."""
+    L.check(L.lib().zvdb_merge_topk_device(d_dist, d_ids, d_counts, G, nq, k, out_dist, out_ids, out_counts,
+                                           stream or None))

@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- batched HNSW search QPS on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--n 1000000] [--dim 128] [--nq 10000] [--k 10] [--ef 64] [--m 16]
+                    [--graph reference|quality] [--sweep]
+
+A "step" is one pass of the hot path (zvdb_search_batch_device: one launch of the layer-0
+best-first kernel) over one batch of nq synthetic Gaussian queries against an index of n
+synthetic Gaussian rows (configs[1] of BASELINE.json: 1M x 128 fp32 L2, M=16, 10k-query batch,
+k=10). Inputs are resident in HBM when the timed region starts; `e2e` repeats the measurement
+through the host-buffer C-ABI call with pinned host buffers (copies inside the timed region).
+
+--impl reference times the reference's CPU algorithm (the C oracle, all host threads) on a
+bounded sample of the same workload. The oracle is executed only in that arm and in the
+`cpu_baseline` leg of the default arm; the measured path never touches it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "batched search QPS at recall@10 (1M x 128 fp32)"
+QUERY_BATCHES = 4   # distinct query batches rotated over the steps
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--n", type=int, default=1_000_000)
+    p.add_argument("--dim", type=int, default=128)
+    p.add_argument("--nq", type=int, default=10_000)
+    p.add_argument("--k", type=int, default=10)
+    p.add_argument("--ef", type=int, default=64)
+    p.add_argument("--m", type=int, default=16)
+    p.add_argument("--graph", default="reference", choices=["reference", "quality"])
+    p.add_argument("--sweep", action="store_true", help="also report the ef sweep 32..512 (untimed extra passes)")
+    p.add_argument("--variant", type=int, default=0, help="search kernel variant: 0 auto, 1 narrow, 2 wide")
+    p.add_argument("--cpu-sample", type=int, default=2000, help="queries in the CPU-baseline sample")
+    return p.parse_args()
+
+
+def make_data(n, dim, nq, seed_x=1, seed_q=2):
+    """X ~ N(0,1) seed 1, Q ~ N(0,1) seed 2 (+ further seeds for the rotated batches)."""
+    X = np.random.default_rng(seed_x).standard_normal((n, dim), dtype=np.float32)
+    Qs = [np.random.default_rng(seed_q + b).standard_normal((nq, dim), dtype=np.float32) for b in range(QUERY_BATCHES)]
+    return X, Qs
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(ef):
+    """dram bytes per launch from the committed ncu --set full capture, if one matches this ef."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(path))
+        return t.get(str(ef))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def recall_at_k(ids, gt):
+    k = gt.shape[1]
+    hit = 0
+    for a, b in zip(ids, gt):
+        hit += len(set(a[:k].tolist()) & set(b.tolist()))
+    return hit / (len(gt) * k)
+
+
+def exact_knn_torch(X_dev, Q, k, chunk=2000):
+    """Ground truth for recall only (outside every timed region): fp32 matmul + topk on the GPU."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xn = (X_dev * X_dev).sum(1)
+    out = []
+    for s in range(0, len(Q), chunk):
+        q = torch.from_numpy(Q[s:s + chunk]).to(X_dev.device)
+        d = xn[None, :] - 2.0 * (q @ X_dev.T)
+        out.append(torch.topk(d, k, dim=1, largest=False).indices.cpu().numpy())
+    return np.concatenate(out).astype(np.uint64)
+
+
+def algorithmic_bytes(evals, pops, row_bytes, m, dim, k):
+    """gathered rows + adjacency rows + query + output, per query, summed."""
+    return int(evals.astype(np.int64).sum()) * row_bytes + int(pops.astype(np.int64).sum()) * m * 4 + \
+        len(evals) * (dim * 4 + k * 12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm on the host cores
+# ---------------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    X, Qs = make_data(args.n, args.dim, args.nq)
+    t0 = time.time()
+    o = O.OracleHNSW(args.m, 200)
+    o.insert_batch(X)
+    adj, _ = o.export_layer(0)
+    log(f"[reference] built {args.n} x {args.dim} index on the host in {time.time() - t0:.1f}s")
+    threads = O.max_threads()
+    sample = min(args.cpu_sample, args.nq)
+    for w in range(args.warmup):
+        O.search_graph(X, adj, Qs[w % QUERY_BATCHES][:sample], args.ef, args.k)
+    t = time.perf_counter()
+    for s in range(args.steps):
+        O.search_graph(X, adj, Qs[s % QUERY_BATCHES][:sample], args.ef, args.k)
+    dt = time.perf_counter() - t
+    qps = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.n}x{args.dim} fp32 L2, M={args.m}, k={args.k}, ef={args.ef}, "
+                               f"graph=reference-insert, {sample}-query sample of the {args.nq}-query batch per step"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} queries/step x {args.steps} steps, one query per thread, no lock"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import zvdb_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    X, Qs = make_data(args.n, args.dim, args.nq)
+    # id-sharding: rank r owns global ids r, r+G, r+2G, ...; one index per shard
+    Xs = X[rank::world] if world > 1 else X
+    t0 = time.time()
+    h = zvdb_b200.HNSW(args.m, 200, device=local)
+    if args.graph == "reference":
+        h.insert_batch(Xs)
+    else:
+        from zvdb_b200 import builder
+        builder.build_quality_graph(h, Xs, args.m)
+    h.sync_device()
+    if args.variant:
+        h.set_kernel_variant(args.variant)
+    build_s = time.time() - t0
+    log(f"[rank {rank}] built {len(Xs)} x {args.dim} ({args.graph} graph) in {build_s:.1f}s")
+
+    nq, k, ef = args.nq, args.k, args.ef
+    row_bytes = ((args.dim + 31) // 32) * 128   # arena rows are padded to 128 bytes
+    ef_shard = max(k, -(-ef // world))   # per-shard pop budget
+    dq = [torch.from_numpy(q).to(dev) for q in Qs]
+    d_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    d_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    d_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    d_pops = torch.empty(nq, dtype=torch.int32, device=dev)
+    d_evals = torch.empty(nq, dtype=torch.int32, device=dev)
+    if world > 1:
+        g_ids = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+        g_dist = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+        g_cnt = torch.empty((world, nq), dtype=torch.int32, device=dev)
+        m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        m_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        m_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+
+    launches = [0]
+
+    def step(b, e=None):
+        e = ef_shard if e is None else e
+        h.search_batch_device(dq[b].data_ptr(), nq, k, e, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(),
+                              d_pops.data_ptr(), d_evals.data_ptr(), id_stride=world, id_base=rank, stream=stream)
+        launches[0] += 1
+        if world > 1:
+            dist.all_gather_into_tensor(g_ids, d_ids)
+            dist.all_gather_into_tensor(g_dist, d_dist)
+            dist.all_gather_into_tensor(g_cnt, d_cnt)
+            zvdb_b200.merge_topk_device(g_dist.data_ptr(), g_ids.data_ptr(), g_cnt.data_ptr(), world, nq, k,
+                                        m_dist.data_ptr(), m_ids.data_ptr(), m_cnt.data_ptr(), stream)
+            launches[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- untimed: counters (roofline numerator) and recall for each query batch -----------------
+    X_dev = torch.from_numpy(X).to(dev) if rank == 0 else None
+    bytes_per_batch, evals_mean, pops_mean, recalls = [], [], [], []
+    for b in range(QUERY_BATCHES):
+        step(b)
+        torch.cuda.synchronize()
+        ev, po = d_evals.cpu().numpy().view(np.uint32), d_pops.cpu().numpy().view(np.uint32)
+        bytes_per_batch.append(algorithmic_bytes(ev, po, row_bytes, args.m, args.dim, k))
+        evals_mean.append(float(ev.mean())); pops_mean.append(float(po.mean()))
+        if rank == 0 and b == 0:
+            gt = exact_knn_torch(X_dev, Qs[0], k)
+            res = (m_ids if world > 1 else d_ids).cpu().numpy().view(np.uint64)
+            recalls.append(recall_at_k(res, gt))
+    sweep = None
+    if args.sweep and rank == 0 and world == 1:
+        sweep = []
+        for e in (32, 64, 128, 256, 512):
+            for _ in range(2):
+                step(0, e)
+            torch.cuda.synchronize()
+            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step(0, e); bb.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(bb)
+            ev, po = d_evals.cpu().numpy().view(np.uint32), d_pops.cpu().numpy().view(np.uint32)
+            by = algorithmic_bytes(ev, po, row_bytes, args.m, args.dim, k)
+            sweep.append({"ef": e, "qps": nq / (ms * 1e-3), "recall_at_10": recall_at_k(d_ids.cpu().numpy().view(np.uint64), gt),
+                          "evals_per_query": float(ev.mean()), "hbm_gbs": by / (ms * 1e-3) / 1e9})
+    del X_dev
+    torch.cuda.empty_cache()
+
+    # ---- timed region: W warm-up steps, then exactly K steps --------------------------------------
+    launches[0] = 0
+    for w in range(args.warmup):
+        step(w % QUERY_BATCHES)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches[0] = 0
+    barrier()
+    t_wall = time.perf_counter()
+    for s in range(args.steps):
+        starts[s].record()
+        step(s % QUERY_BATCHES)
+        ends[s].record()
+    barrier()
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = starts[0].elapsed_time(ends[-1])             # device time of the whole K-step region
+    kern_ms = [starts[s].elapsed_time(ends[s]) for s in range(args.steps)]
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    gpu_launches = launches[0]
+
+    # ---- e2e: the host-buffer C-ABI call, pinned host memory, copies inside the timed region -----
+    e2e = None
+    if world == 1:
+        hq = [torch.from_numpy(q).pin_memory() for q in Qs]
+        h_ids = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+        h_dist = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+        h_cnt = torch.empty(nq, dtype=torch.int32).pin_memory()
+        for w in range(args.warmup):
+            h.search_batch_ptr(hq[w % QUERY_BATCHES].data_ptr(), nq, args.dim, k, ef, h_ids.data_ptr(),
+                               h_dist.data_ptr(), h_cnt.data_ptr())
+        torch.cuda.synchronize()
+        t_e = time.perf_counter()
+        for s in range(args.steps):
+            h.search_batch_ptr(hq[s % QUERY_BATCHES].data_ptr(), nq, args.dim, k, ef, h_ids.data_ptr(),
+                               h_dist.data_ptr(), h_cnt.data_ptr())
+        torch.cuda.synchronize()
+        e_dt = time.perf_counter() - t_e
+        e2e = {"value": nq * args.steps / e_dt, "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4,
+               "d2h_bytes_per_step": nq * k * 12 + nq * 4}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline: the oracle on the host cores, bounded sample of the same workload ---------
+    cpu = None
+    if world == 1:
+        from oracle import oracle as O
+        O.build()
+        adj, _ = h.export_layer(0)
+        sample = min(args.cpu_sample, nq)
+        O.search_graph(X, adj, Qs[1][:256], ef, k)                       # warm the threads
+        t_c = time.perf_counter()
+        ref = O.search_graph(X, adj, Qs[0][:sample], ef, k)
+        c_dt = time.perf_counter() - t_c
+        # parity spot-check of the measured configuration (checker, not the thing measured)
+        step(0)
+        torch.cuda.synchronize()
+        got = d_ids.cpu().numpy().view(np.uint64)[:sample]
+        same = float((got == ref["ids"].astype(np.uint64)).mean())
+        ev_same = bool(np.array_equal(d_evals.cpu().numpy().view(np.uint32)[:sample], ref["evals"]))
+        cpu = {"value": sample / c_dt, "unit": "queries/s", "cores": O.max_threads(), "kind": "port",
+               "sample": f"first {sample} queries of batch 0, same graph/ef/k, one query per thread, no lock",
+               "ids_equal_frac_vs_gpu": same, "evals_equal_vs_gpu": ev_same}
+
+    peak, peak_src = load_peaks()
+    avg_kernel_s = float(np.mean(kern_ms)) * 1e-3
+    mean_bytes = float(np.mean([bytes_per_batch[s % QUERY_BATCHES] for s in range(args.steps)]))
+    achieved = mean_bytes / avg_kernel_s / 1e9
+    qps = nq * args.steps / (dev_ms_max * 1e-3)
+    line = {
+        "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.n}x{args.dim} fp32 L2 synthetic Gaussian, M={args.m}, {nq}-query batch, k={k}, "
+                               f"ef={ef}" + (f" ({ef_shard}/shard, id-sharded over {world} GPUs, all-gather + merge)" if world > 1 else ""),
+                   "graph": "reference insert (hnsw.zig:73-170)" if args.graph == "reference" else "quality builder",
+                   "l2_policy": f"index {args.n * args.dim * 4 / 1e6:.0f} MB > 126 MB L2; {QUERY_BATCHES} query batches rotated",
+                   "recall_at_10": recalls[0] if recalls else None,
+                   "evals_per_query": float(np.mean(evals_mean)), "pops_per_query": float(np.mean(pops_mean)),
+                   "build_seconds": build_s, "wall_ms_per_step": 1e3 * wall / args.steps},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": load_traffic(ef), "peak_source": peak_src, "kernel": "search_layer0_kernel",
+                     "algorithmic_bytes_per_launch": mean_bytes, "avg_launch_ms": avg_kernel_s * 1e3},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+    }
+    if sweep:
+        line["sweep"] = sweep
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,15 @@ ZVDB_API int zvdb_export_layer(const zvdb_index *ix, uint32_t layer, uint32_t *a
 ZVDB_API int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim,
                              const uint64_t *offsets, const uint32_t *nbrs, uint64_t entry);
 
+/* Replace the whole index by a graph BUILT ON THE GPU from per-node candidate lists (SURVEY 8f
+ * rank 1; no reference counterpart -- the reference's insert stays zvdb_insert). cand[n x K]
+ * holds K <= 128 candidate neighbour ids per node (e.g. approximate k-NN; order, self-references,
+ * duplicates and ids >= n are tolerated), in host memory or, if cand_on_device != 0, in device
+ * memory. The result keeps the reference's layout: <= m layer-0 neighbours per node, entry point
+ * node 0. Algorithm: zvdb_b200/csrc/builder.cuh. */
+ZVDB_API int zvdb_build_from_candidates(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim,
+                                        const uint32_t *cand, uint32_t K, int cand_on_device);
+
 /* ---- search ------------------------------------------------------------------------------ */
 
 /* HNSW(T).search(query, k), hnsw.zig:194-236: best-first from the entry point over layer 0,
@@ -139,8 +148,11 @@ ZVDB_API int zvdb_search_batch_device(zvdb_index *ix, const float *d_queries, ui
 /* Push pending host-side inserts to the device now (otherwise done by the next search). */
 ZVDB_API int zvdb_sync_device(zvdb_index *ix);
 
-/* Launch shape override for tuning: warps cooperating on one query (0 = automatic). */
-ZVDB_API int zvdb_set_warps_per_query(zvdb_index *ix, uint32_t warps);
+/* Search-kernel variant override for tuning and tests; results are identical for every value.
+ * bits 0-1: 0 = automatic, 1 = narrow (8 row loads in flight per warp), 2 = wide (16 in flight);
+ * bits 2-3: where the exact visited set lives: 0 = automatic, 1 = shared-memory hash table,
+ *           2 = per-CTA bitmap in global memory (persistent CTAs; used for large ef * m). */
+ZVDB_API int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant);
 
 /* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */
 ZVDB_API uint64_t zvdb_kernel_launches(const zvdb_index *ix);

@@ -73,6 +73,9 @@ def lib():
         L.orc_max_threads.restype = i32
         L.orc_distance_f32.restype = C.c_float
         L.orc_distance_f32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), i32, i32]
+        L.orc_dist_many_f32.restype = None
+        L.orc_dist_many_f32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), i32, C.POINTER(C.c_uint32), sz,
+                                        i32, C.POINTER(C.c_float)]
         L.orc_bruteforce_f32.argtypes = [C.POINTER(C.c_float), sz, i32, C.POINTER(C.c_float), sz, sz, i32, i32,
                                          C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         L.orc_merge_topk.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), i32,
@@ -94,6 +97,16 @@ def distance(a, b, mode=DIST_SEQ) -> np.float32:
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)
     return np.float32(lib().orc_distance_f32(_ptr(a, C.c_float), _ptr(b, C.c_float), a.size, mode))
+
+
+def dist_many(a, points, ids, mode=DIST_SEQ) -> np.ndarray:
+    """Distances from vector `a` to rows points[ids] (points must be C-contiguous float32)."""
+    a = np.ascontiguousarray(a, np.float32)
+    ids = np.ascontiguousarray(ids, np.uint32)
+    out = np.empty(len(ids), np.float32)
+    lib().orc_dist_many_f32(_ptr(a, C.c_float), _ptr(points, C.c_float), points.shape[1], _ptr(ids, C.c_uint32),
+                            len(ids), mode, _ptr(out, C.c_float))
+    return out
 
 
 class OracleHNSW:

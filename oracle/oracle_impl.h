@@ -41,16 +41,18 @@ static inline T SFX(orc_dist_seq)(const T *a, const T *b, int dim) {
 
 #ifdef ORC_T_IS_F32
 /* GPU summation order, restated on the CPU so the kernel can be checked bit-for-bit
- * (zvdb_b200/csrc/search_kernel.cuh: row_distance). The row is cut into 16-byte chunks of 4
- * floats; lane l of a 32-lane warp owns chunks l, l+32, l+64, ...; inside a chunk it
- * accumulates x,y,z,w in order with an unfused multiply and add; the 32 lane sums are then
- * combined by an xor butterfly with offsets 16,8,4,2,1. Elements past `dim` are zero padding.
+ * (zvdb_b200/csrc/search_kernel.cuh: accumulate_chunk / rows_distance). The row is cut into
+ * 16-byte chunks of 4 floats (x,y,z,w); lane l of a 32-lane warp owns chunks l, l+32, l+64, ...
+ * and keeps two running sums: A0 takes x then z, A1 takes y then w, each by ONE FUSED multiply-add
+ * per element (the kernel uses packed fma.rn.f32x2); the difference q - v is rounded once, as in
+ * hnsw.zig:188. The lane's partial is A0 + A1; the 32 partials are combined by an xor butterfly
+ * with offsets 16,8,4,2,1. Elements past `dim` are zero padding.
  * metric: 0 = squared L2, 1 = cosine (1 - dot, rows pre-normalised), 2 = dot (-dot). */
 static inline float orc_dist_tree_metric(const float *a, const float *b, int dim, int metric) {
     float lane[32];
     const int chunks = (dim + 3) / 4;
     for (int l = 0; l < 32; ++l) {
-        float acc = 0.0f;
+        float acc[2] = {0.0f, 0.0f};
         for (int c = l; c < chunks; c += 32) {
             for (int e = 0; e < 4; ++e) {
                 const int i = c * 4 + e;
@@ -58,15 +60,13 @@ static inline float orc_dist_tree_metric(const float *a, const float *b, int dim
                 const float y = i < dim ? b[i] : 0.0f;
                 if (metric == 0) {
                     const float d = x - y;
-                    const float p = d * d;
-                    acc = acc + p;
+                    acc[e & 1] = fmaf(d, d, acc[e & 1]);
                 } else {
-                    const float p = x * y;
-                    acc = acc + p;
+                    acc[e & 1] = fmaf(x, y, acc[e & 1]);
                 }
             }
         }
-        lane[l] = acc;
+        lane[l] = acc[0] + acc[1];
     }
     for (int off = 16; off >= 1; off >>= 1) {
         float nxt[32];
@@ -74,7 +74,7 @@ static inline float orc_dist_tree_metric(const float *a, const float *b, int dim
         memcpy(lane, nxt, sizeof(lane));
     }
     if (metric == 1) return 1.0f - lane[0];
-    if (metric == 2) return -lane[0];
+    if (metric == 2) return 0.0f - lane[0];
     return lane[0];
 }
 static inline float orc_dist_tree_f32(const float *a, const float *b, int dim) {

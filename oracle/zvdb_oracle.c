@@ -117,7 +117,9 @@
         if (k > ef) k = ef;                                                                           \
         _Pragma("omp parallel num_threads(nthreads > 0 ? nthreads : omp_get_max_threads())")          \
         {                                                                                             \
-            orc_scratch_##S sc; memset(&sc, 0, sizeof(sc));                                           \
+            /* per-thread scratch (visited stamps, heap) lives across calls: a 4n-byte stamp array    \
+             * per call would dominate short timed samples */                                         \
+            static __thread orc_scratch_##S sc;                                                       \
             uint32_t *tid = (uint32_t *)malloc((ef + 1) * sizeof(uint32_t));                          \
             T *td = (T *)malloc((ef + 1) * sizeof(T));                                                \
             _Pragma("omp for schedule(dynamic, 8)")                                                   \
@@ -142,7 +144,7 @@
                 if (pops) pops[qi] = p;                                                               \
                 if (evals) evals[qi] = e;                                                             \
             }                                                                                         \
-            orc_scratch_free_##S(&sc); free(tid); free(td);                                           \
+            free(tid); free(td);                                                                      \
         }                                                                                             \
         return err ? -1 : 0;                                                                          \
     }
@@ -160,6 +162,12 @@ EXPORT int orc_max_threads(void) { return omp_get_max_threads(); }
 /* Single-pair distance, exposed so tests can pin the two summation orders. */
 EXPORT float orc_distance_f32(const float *a, const float *b, int dim, int mode) {
     return orc_dist_f32(mode, a, b, dim);
+}
+
+/* Distances from one vector to a list of rows (used by tests/builder_ref.py). */
+EXPORT void orc_dist_many_f32(const float *a, const float *pts, int dim, const uint32_t *ids, size_t count,
+                              int mode, float *out) {
+    for (size_t i = 0; i < count; ++i) out[i] = orc_dist_f32(mode, a, pts + (size_t)ids[i] * dim, dim);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -207,32 +215,33 @@ EXPORT int orc_bruteforce_f32(const float *pts, size_t n, int dim, const float *
 
 /* ------------------------------------------------------------------------------------------
  * Oracle for the shard merge (K5): G per-shard result lists of k (distance, global id)
- * pairs, each sorted ascending, counts[g*nq+q] valid entries; output the k smallest by
- * (distance, global id). Layout of the gathered input: [G][nq][k].
+ * pairs with counts[g*nq+q] valid entries each; output the k smallest of their union under the
+ * strict order (distance, global id). A shard's own list is ordered by (distance, pop order), so
+ * exact ties inside it need not be id-ordered: the union is sorted, not head-merged.
+ * Layout of the gathered input: [G][nq][k].
  * ------------------------------------------------------------------------------------------ */
+typedef struct { float d; uint64_t id; } orc_pair;
+static int orc_pair_cmp(const void *a, const void *b) {
+    const orc_pair *x = (const orc_pair *)a, *y = (const orc_pair *)b;
+    if (x->d < y->d) return -1;
+    if (x->d > y->d) return 1;
+    return x->id < y->id ? -1 : (x->id > y->id ? 1 : 0);
+}
 EXPORT void orc_merge_topk(const float *d_in, const uint64_t *id_in, const uint32_t *cnt_in, int G,
                            size_t nq, size_t k, float *d_out, uint64_t *id_out, uint32_t *cnt_out) {
+    orc_pair *buf = (orc_pair *)malloc((size_t)G * k * sizeof(orc_pair) + 1);
     for (size_t q = 0; q < nq; ++q) {
-        size_t pos[64] = {0};
         size_t len = 0;
-        while (len < k) {
-            int best = -1;
-            for (int g = 0; g < G; ++g) {
-                const size_t base = ((size_t)g * nq + q);
-                if (pos[g] >= cnt_in[base]) continue;
-                if (best < 0) { best = g; continue; }
-                const size_t bb = ((size_t)best * nq + q);
-                const float dg = d_in[base * k + pos[g]], db = d_in[bb * k + pos[best]];
-                const uint64_t ig = id_in[base * k + pos[g]], ib = id_in[bb * k + pos[best]];
-                if (dg < db || (dg == db && ig < ib)) best = g;
-            }
-            if (best < 0) break;
-            const size_t bb = ((size_t)best * nq + q);
-            d_out[q * k + len] = d_in[bb * k + pos[best]];
-            id_out[q * k + len] = id_in[bb * k + pos[best]];
-            pos[best]++; len++;
+        for (int g = 0; g < G; ++g) {
+            const size_t base = (size_t)g * nq + q;
+            const size_t c = cnt_in[base] < k ? cnt_in[base] : k;
+            for (size_t j = 0; j < c; ++j) { buf[len].d = d_in[base * k + j]; buf[len].id = id_in[base * k + j]; ++len; }
         }
+        qsort(buf, len, sizeof(orc_pair), orc_pair_cmp);
+        if (len > k) len = k;
+        for (size_t j = 0; j < len; ++j) { d_out[q * k + j] = buf[j].d; id_out[q * k + j] = buf[j].id; }
         for (size_t j = len; j < k; ++j) { d_out[q * k + j] = 0.0f; id_out[q * k + j] = ~0ull; }
         cnt_out[q] = (uint32_t)len;
     }
+    free(buf);
 }

@@ -261,12 +261,12 @@ def test_search_bit_exact_vs_oracle(zv, oracle, n, dim, m, k, ef):
     h.deinit()
 
 
-@pytest.mark.parametrize("warps", [1, 2, 4, 8])
-def test_team_width_does_not_change_results(zv, oracle, warps):
+@pytest.mark.parametrize("warps", [0b0101, 0b0110, 0b1001, 0b1010])   # {smem hash, global bitmap} x {narrow, wide}
+def test_kernel_variant_does_not_change_results(zv, oracle, warps):
     X, h, adj = _build_pair(zv, oracle, 6000, 128, 16, 43)
     Q = _gauss(300, 128, 44)
     base = h.search_batch(Q, 10, 96, counters=True)
-    h.set_warps_per_query(warps)
+    h.set_kernel_variant(warps)
     got = h.search_batch(Q, 10, 96, counters=True)
     for a, b in zip(base, got):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
@@ -392,3 +392,43 @@ def test_shard_merge_kernel(zv, oracle):
         assert np.array_equal(oc.cpu().numpy().view(np.uint32), co)
         assert np.array_equal(oi.cpu().numpy().view(np.uint64), io)
         assert np.array_equal(od.cpu().numpy(), do)
+
+
+# ------------------------------------------------------------------------------------------------
+# the GPU graph builder (extension; checked against tests/builder_ref.py, not against hnsw.zig)
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,dim,m,K", [(1500, 32, 8, 24), (1200, 128, 16, 48), (600, 200, 4, 128)])
+def test_builder_matches_cpu_statement(zv, oracle, n, dim, m, K):
+    from builder_ref import build_ref
+    X = _gauss(n, dim, 61)
+    nn, _ = oracle.bruteforce(X, X, K)          # includes self at rank 0: the builder must drop it
+    cand = nn.astype(np.uint32)
+    cand[::7, 3] = 0xFFFFFFFF                   # padding and duplicates are tolerated
+    cand[::5, 5] = cand[::5, 4]
+    h = zv.HNSW(m, 200)
+    h.build_from_candidates(X, cand)
+    adj, deg = h.export_layer(0)
+    ref = build_ref(oracle, X, cand, m)
+    assert np.array_equal(adj, ref)
+    assert h.entry_point == 0 and h.count() == n
+    # the built graph is searched by the same kernel with the same parity
+    Q = _gauss(64, dim, 62)
+    ids, dist, counts, pops, evals = h.search_batch(Q, 5, 30, counters=True)
+    r = oracle.search_graph(X, adj, Q, 30, 5, dist_mode=oracle.DIST_TREE, heap_mode=oracle.HEAP_DET)
+    assert np.array_equal(ids, r["ids"].astype(np.uint64)) and np.array_equal(evals, r["evals"])
+    h.deinit()
+
+
+def test_builder_graph_reaches_useful_recall(zv, oracle):
+    n, dim, m = 20000, 64, 16
+    X = _gauss(n, dim, 63)
+    nn, _ = oracle.bruteforce(X, X, 49)
+    h = zv.HNSW(m, 200)
+    h.build_from_candidates(X, nn[:, 1:].astype(np.uint32))
+    Q = _gauss(200, dim, 64)
+    gt, _ = oracle.bruteforce(X, Q, 10)
+    ids, _, _ = h.search_batch(Q, 10, 256)
+    rec = np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(Q))])
+    assert rec > 0.9, rec
+    h.deinit()

@@ -34,11 +34,12 @@ SIGNATURES = {
     "zvdb_node_level": (C.c_int32, [_vp, _u64]),
     "zvdb_export_layer": (_i32, [_vp, _u32, _pu32, _pu32]),
     "zvdb_load_graph": (_i32, [_vp, _pf, _u64, _u32, _pu64, _pu32, _u64]),
+    "zvdb_build_from_candidates": (_i32, [_vp, _pf, _u64, _u32, _vp, _u32, _i32]),
     "zvdb_search": (_i32, [_vp, _pf, _u32, _u32, _pu64, _pf, _pu32]),
     "zvdb_search_batch": (_i32, [_vp, _vp, _u64, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "zvdb_search_batch_device": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp]),
     "zvdb_sync_device": (_i32, [_vp]),
-    "zvdb_set_warps_per_query": (_i32, [_vp, _u32]),
+    "zvdb_set_kernel_variant": (_i32, [_vp, _u32]),
     "zvdb_kernel_launches": (_u64, [_vp]),
     "zvdb_merge_topk_device": (_i32, [_vp, _vp, _vp, _u32, _u64, _u32, _vp, _vp, _vp, _vp]),
     "zvdb_last_error": (C.c_char_p, []),

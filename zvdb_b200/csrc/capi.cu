@@ -12,6 +12,7 @@
 #include "../../include/zvdb_b200.h"
 #include "host_graph.hpp"
 #include "search_kernel.cuh"
+#include "builder.cuh"
 
 namespace zvdb {
 
@@ -76,8 +77,9 @@ struct zvdb_index {
     uint64_t cap_rows = 0, n_dev = 0;
     DevBuf<float> q_buf, dist_buf;
     DevBuf<uint64_t> ids_buf;
-    DevBuf<uint32_t> cnt_buf, pops_buf, evals_buf, scat_rows, scat_ids;
-    uint32_t warps_per_query = 0;
+    DevBuf<uint32_t> cnt_buf, pops_buf, evals_buf, scat_rows, scat_ids, bitmap_buf, vlog_buf;
+    uint32_t variant = 0;           // 0 automatic, 1 narrow, 2 wide (tuning/testing)
+    uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap
     std::atomic<uint64_t> launches{0};
 };
 
@@ -146,27 +148,36 @@ static int sync_device_locked(zvdb_index *ix) {
 
 // ---- K1 launch ------------------------------------------------------------------------------
 
-template <int CPL, int METRIC>
-static cudaError_t launch_search_inst(const SearchParams &p, unsigned threads, size_t smem, cudaStream_t s) {
-    auto kern = search_layer0_kernel<CPL, METRIC>;
+template <int CPL, int METRIC, bool WIDE, int VIS>
+static cudaError_t launch_search_inst(const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    auto kern = search_layer0_kernel<CPL, METRIC, WIDE, VIS>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
-    kern<<<p.nq, threads, smem, s>>>(p);
+    kern<<<grid, 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-template <int METRIC>
-static cudaError_t launch_search_metric(int cpl, const SearchParams &p, unsigned threads, size_t smem, cudaStream_t s) {
+template <int METRIC, bool WIDE, int VIS>
+static cudaError_t launch_search_metric(int cpl, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     switch (cpl) {
-        case 1: return launch_search_inst<1, METRIC>(p, threads, smem, s);
-        case 2: return launch_search_inst<2, METRIC>(p, threads, smem, s);
-        case 4: return launch_search_inst<4, METRIC>(p, threads, smem, s);
-        case 6: return launch_search_inst<6, METRIC>(p, threads, smem, s);
-        case 8: return launch_search_inst<8, METRIC>(p, threads, smem, s);
+        case 1: return launch_search_inst<1, METRIC, WIDE, VIS>(p, grid, smem, s);
+        case 2: return launch_search_inst<2, METRIC, WIDE, VIS>(p, grid, smem, s);
+        case 4: return launch_search_inst<4, METRIC, WIDE, VIS>(p, grid, smem, s);
+        case 6: return launch_search_inst<6, METRIC, WIDE, VIS>(p, grid, smem, s);
+        case 8: return launch_search_inst<8, METRIC, WIDE, VIS>(p, grid, smem, s);
     }
     return cudaErrorInvalidValue;
+}
+
+template <bool WIDE, int VIS>
+static cudaError_t launch_search_wv(int metric, int cpl, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    switch (metric) {
+        case 0: return launch_search_metric<kMetricL2, WIDE, VIS>(cpl, p, grid, smem, s);
+        case 1: return launch_search_metric<kMetricCos, WIDE, VIS>(cpl, p, grid, smem, s);
+        default: return launch_search_metric<kMetricDot, WIDE, VIS>(cpl, p, grid, smem, s);
+    }
 }
 
 // Device buffers in, device buffers out, no synchronisation. Caller holds the lock and has synced
@@ -186,34 +197,54 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     p.row_chunks = g.row_floats / 4;
     p.m = g.m; p.n = static_cast<uint32_t>(g.n); p.entry = static_cast<uint32_t>(g.entry); p.dim = g.dim;
     p.nq = static_cast<uint32_t>(nq); p.k = k; p.ef = ef;
+    const uint32_t chunks_per_lane = (p.row_chunks + 31) / 32;
+    if (chunks_per_lane > 8) return fail(ZVDB_ERR_UNSUPPORTED, "dim > 1024 is not built into the search kernel");
+    const int cpl = chunks_per_lane <= 1 ? 1 : chunks_per_lane <= 2 ? 2 : chunks_per_lane <= 4 ? 4 : chunks_per_lane <= 6 ? 6 : 8;
+
     const uint64_t bound = std::min<uint64_t>(g.n, 1ull + static_cast<uint64_t>(ef) * g.m);   // visited-set maximum
-    const uint64_t slots = bound + bound / 3 + 16;
-    const uint64_t hash_words = std::max<uint64_t>(slots, 2ull * next_pow2(ef));
-    const uint64_t smem = static_cast<uint64_t>(ef) * 8 + 32 * 8 + hash_words * 4 + 32 * 4 + 32 * 4 + 16;
+    const uint64_t slots = bound + bound / 4 + 16;
+    const uint64_t cand_cap = std::max<uint64_t>(2, next_pow2(ef));   // >= ef, even (alignment), reused by the final sort
+    const uint64_t smem_lists = (((static_cast<uint64_t>(ef) + 1) & ~1ull) + cand_cap) * 8 + kPoolCap * 8 + 32 * 4 + kPoolCap * 4 + 16;
+    const uint64_t smem_hash = smem_lists + slots * 4;
+    auto ctas_for = [](uint64_t smem) { return std::min<uint64_t>(32, (227ull * 1024) / (smem + 1024)); };
+    // Where the exact visited set lives. On chip while that still leaves >= 20 warps per SM; beyond
+    // that a per-CTA bitmap in global memory keeps residency up (one atomicOr per neighbour).
+    int vis = (smem_hash <= ix->smem_optin && ctas_for(smem_hash) >= 20) ? kVisSmemHash : kVisGlobalBitmap;
+    if (ix->visited_mode == 1) vis = kVisSmemHash;
+    if (ix->visited_mode == 2) vis = kVisGlobalBitmap;
+    const uint64_t smem = vis == kVisSmemHash ? smem_hash : smem_lists;
     if (smem > ix->smem_optin) {
         char buf[256];
         snprintf(buf, sizeof buf, "search needs %llu bytes of shared memory per query (ef=%u, m=%u); this device allows %zu. Lower ef.",
                  static_cast<unsigned long long>(smem), ef, g.m, ix->smem_optin);
         return fail(ZVDB_ERR_UNSUPPORTED, buf);
     }
-    p.slots = static_cast<uint32_t>(slots); p.hash_words = static_cast<uint32_t>(hash_words);
-    const uint32_t chunks_per_lane = (p.row_chunks + 31) / 32;
-    int cpl = chunks_per_lane <= 1 ? 1 : chunks_per_lane <= 2 ? 2 : chunks_per_lane <= 4 ? 4 : chunks_per_lane <= 6 ? 6 : 8;
-    if (chunks_per_lane > 8) return fail(ZVDB_ERR_UNSUPPORTED, "dim > 1024 is not built into the search kernel");
-    // Team width: enough warps per SM to cover HBM latency even when shared memory limits the CTAs per SM.
-    uint32_t W = ix->warps_per_query;
-    if (W == 0) {
-        const uint64_t ctas_per_sm = std::min<uint64_t>(32, (227ull * 1024) / (smem + 1024));
-        W = 1;
-        while (W < 8 && ctas_per_sm * W < 32) W *= 2;
+    p.slots = static_cast<uint32_t>(slots); p.hash_words = static_cast<uint32_t>(slots);
+    p.cand_cap = static_cast<uint32_t>(cand_cap);
+    // One warp per query. When shared memory already caps residency at <= 16 warps per SM, use the
+    // variant that keeps twice as many row loads in flight per warp (more registers per thread).
+    bool wide = ctas_for(smem) <= 16;
+    if (ix->variant == 1) wide = false;
+    if (ix->variant == 2) wide = true;
+    unsigned grid = static_cast<unsigned>(nq);
+    if (vis == kVisGlobalBitmap) {
+        const uint64_t resident = std::min<uint64_t>(ctas_for(smem), wide ? 16 : 32) * ix->num_sms;
+        grid = static_cast<unsigned>(std::min<uint64_t>(nq, resident));          // persistent CTAs
+        const uint64_t bm_words = (g.n + 31) / 32;
+        const uint64_t need = grid * bm_words;
+        if (need > ix->bitmap_buf.cap) {
+            ZV_CUDA(ix->bitmap_buf.reserve(need));
+            ZV_CUDA(cudaMemsetAsync(ix->bitmap_buf.p, 0, ix->bitmap_buf.cap * sizeof(uint32_t), s));
+        }
+        ZV_CUDA(ix->vlog_buf.reserve(grid * bound));
+        p.gbitmap = ix->bitmap_buf.p; p.glog = ix->vlog_buf.p;
+        p.bm_words = static_cast<uint32_t>(bm_words); p.log_cap = static_cast<uint32_t>(bound);
     }
-    W = std::min<uint32_t>(std::max<uint32_t>(W, 1), 8);
     cudaError_t e;
-    switch (g.metric) {
-        case 0: e = launch_search_metric<kMetricL2>(cpl, p, W * 32, smem, s); break;
-        case 1: e = launch_search_metric<kMetricCos>(cpl, p, W * 32, smem, s); break;
-        default: e = launch_search_metric<kMetricDot>(cpl, p, W * 32, smem, s); break;
-    }
+    if (vis == kVisSmemHash) e = wide ? launch_search_wv<true, kVisSmemHash>(g.metric, cpl, p, grid, smem, s)
+                                      : launch_search_wv<false, kVisSmemHash>(g.metric, cpl, p, grid, smem, s);
+    else e = wide ? launch_search_wv<true, kVisGlobalBitmap>(g.metric, cpl, p, grid, smem, s)
+                  : launch_search_wv<false, kVisGlobalBitmap>(g.metric, cpl, p, grid, smem, s);
     ix->launches++;
     ZV_CUDA(e);
     return ZVDB_OK;
@@ -271,6 +302,27 @@ __global__ void merge_topk_kernel(const float *__restrict__ d_dist, const uint64
     if (tid == 0) out_counts[q] = nres;
 }
 
+template <int CPL, int METRIC>
+static void launch_build_stage(int stage, const BuildParams &bp, cudaStream_t s) {
+    if (stage == 1) build_forward_kernel<CPL, METRIC><<<bp.n, 32, 0, s>>>(bp);
+    else build_final_kernel<CPL, METRIC><<<bp.n, 32, 0, s>>>(bp);
+}
+template <int METRIC>
+static void launch_build_metric(int cpl, int stage, const BuildParams &bp, cudaStream_t s) {
+    switch (cpl) {
+        case 1: launch_build_stage<1, METRIC>(stage, bp, s); break;
+        case 2: launch_build_stage<2, METRIC>(stage, bp, s); break;
+        case 4: launch_build_stage<4, METRIC>(stage, bp, s); break;
+        case 6: launch_build_stage<6, METRIC>(stage, bp, s); break;
+        default: launch_build_stage<8, METRIC>(stage, bp, s); break;
+    }
+}
+static void launch_build(int metric, int cpl, int stage, const BuildParams &bp, cudaStream_t s) {
+    if (metric == 0) launch_build_metric<kMetricL2>(cpl, stage, bp, s);
+    else if (metric == 1) launch_build_metric<kMetricCos>(cpl, stage, bp, s);
+    else launch_build_metric<kMetricDot>(cpl, stage, bp, s);
+}
+
 }  // namespace zvdb
 
 // ================================ exported C ABI ================================================
@@ -317,7 +369,7 @@ void zvdb_destroy(zvdb_index *ix) {
     if (ix->stream) { cudaStreamSynchronize(ix->stream); cudaStreamDestroy(ix->stream); }
     cudaFree(ix->d_arena); cudaFree(ix->d_adj);
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
-    ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_();
+    ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_();
     delete ix;
 }
 
@@ -405,21 +457,12 @@ int zvdb_export_layer(const zvdb_index *cix, uint32_t layer, uint32_t *adj, uint
     return ZVDB_OK;
 }
 
-int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, const uint64_t *offsets,
-                    const uint32_t *nbrs, uint64_t entry) {
-    if (!ix || (n && (!points || !offsets))) return fail(ZVDB_ERR_INVALID, "null argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+// Replace the node set by n rows of `points` (levels 0, no edges yet, entry = `entry`).
+static int set_points_locked(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, uint64_t entry) {
     HostGraph &g = ix->g;
-    if (dim == 0 || dim > 1024) return fail(ZVDB_ERR_UNSUPPORTED, "load_graph: dim must be in 1..1024");
-    if (g.dim != 0 && g.dim != dim && g.n != 0) return fail(ZVDB_ERR_DIM_MISMATCH, "Mismatched dimensions in distance calculation");
-    if (n >= 0xFFFFFFFEull) return fail(ZVDB_ERR_UNSUPPORTED, "load_graph: more than 2^32-2 nodes in one shard");
-    if (n && entry >= n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "load_graph: entry out of range");
-    for (uint64_t i = 0; i < n; ++i) {
-        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > g.m)
-            return fail(ZVDB_ERR_INVALID, "load_graph: a node has more than m neighbours (or offsets decrease)");
-    }
-    for (uint64_t e = 0; n && e < offsets[n]; ++e)
-        if (nbrs[e] >= n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "load_graph: neighbour id out of range");
+    if (dim == 0 || dim > 1024) return fail(ZVDB_ERR_UNSUPPORTED, "dim must be in 1..1024");
+    if (n >= 0xFFFFFFFEull) return fail(ZVDB_ERR_UNSUPPORTED, "more than 2^32-2 nodes in one shard");
+    if (n && entry >= n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "entry out of range");
     cudaSetDevice(ix->device);
     g.reset_nodes();
     g.fix_dim(dim);
@@ -427,7 +470,7 @@ int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t di
         g.adj0.assign(n * g.m, kInvalidId);
         g.level.assign(n, 0);
         g.upper_off.assign(n, ~0ull);
-    } catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "load_graph: out of memory"); }
+    } catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "out of memory"); }
     const uint64_t nchunks = (n + g.rows_per_chunk - 1) / g.rows_per_chunk;
     for (uint64_t c = 0; c < nchunks; ++c) {
         float *p = nullptr;
@@ -447,12 +490,95 @@ int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t di
             }
         }
         for (uint32_t t = dim; t < g.row_floats; ++t) row[t] = 0.0f;
-        const uint64_t b = offsets[i], e = offsets[i + 1];
-        for (uint64_t t = b; t < e; ++t) g.adj0[i * g.m + (t - b)] = nbrs[t];
     }
     g.has_entry = n > 0; g.entry = entry; g.max_level = 0;
     g.rows_uploaded = 0; g.adj_all_dirty = true;
     ix->n_dev = 0;
+    return ZVDB_OK;
+}
+
+int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, const uint64_t *offsets,
+                    const uint32_t *nbrs, uint64_t entry) {
+    if (!ix || (n && (!points || !offsets))) return fail(ZVDB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    HostGraph &g = ix->g;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > g.m)
+            return fail(ZVDB_ERR_INVALID, "load_graph: a node has more than m neighbours (or offsets decrease)");
+    }
+    for (uint64_t e = 0; n && e < offsets[n]; ++e)
+        if (nbrs[e] >= n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "load_graph: neighbour id out of range");
+    int rc = set_points_locked(ix, points, n, dim, entry);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t b = offsets[i], e = offsets[i + 1];
+        for (uint64_t t = b; t < e; ++t) g.adj0[i * g.m + (t - b)] = nbrs[t];
+    }
+    return ZVDB_OK;
+}
+
+int zvdb_build_from_candidates(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, const uint32_t *cand,
+                               uint32_t K, int cand_on_device) {
+    if (!ix || (n && (!points || !cand))) return fail(ZVDB_ERR_INVALID, "null argument");
+    if (K == 0 || K > kBuildBuf) return fail(ZVDB_ERR_UNSUPPORTED, "build: K must be in 1..128");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    HostGraph &g = ix->g;
+    if (g.m > 64) return fail(ZVDB_ERR_UNSUPPORTED, "build: m must be <= 64");
+    int rc = set_points_locked(ix, points, n, dim, 0);   // entry point = node 0, as in the reference
+    if (rc || n == 0) return rc;
+    g.adj_all_dirty = false;                             // the table is produced on the device
+    rc = ensure_capacity(ix, n);
+    if (rc) return rc;
+    cudaStream_t s = ix->stream;
+    for (uint64_t r = 0; r < n;) {                       // arena rows up
+        const uint64_t chunk = r / g.rows_per_chunk;
+        const uint64_t end = std::min<uint64_t>(n, (chunk + 1) * g.rows_per_chunk);
+        ZV_CUDA(cudaMemcpyAsync(ix->d_arena + r * g.row_floats, g.point(r), (end - r) * g.row_floats * sizeof(float), cudaMemcpyHostToDevice, s));
+        r = end;
+    }
+    DevBuf<uint32_t> d_cand, d_fw, d_indeg, d_rev;
+    DevBuf<uint64_t> d_off;
+    const uint32_t *cand_dev = cand;
+    if (!cand_on_device) {
+        ZV_CUDA(d_cand.reserve(n * K));
+        ZV_CUDA(cudaMemcpyAsync(d_cand.p, cand, n * K * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        cand_dev = d_cand.p;
+    }
+    auto cleanup = [&]() { d_cand.free_(); d_fw.free_(); d_indeg.free_(); d_rev.free_(); d_off.free_(); };
+#define ZV_B(expr) do { cudaError_t e2__ = (expr); if (e2__ != cudaSuccess) { cleanup(); ZV_CUDA(e2__); } } while (0)
+    ZV_B(d_fw.reserve(n * g.m));
+    ZV_B(d_indeg.reserve(2 * n));
+    ZV_B(d_off.reserve(n + 1));
+    ZV_B(cudaMemsetAsync(d_indeg.p, 0, 2 * n * sizeof(uint32_t), s));
+    BuildParams bp{};
+    bp.arena = reinterpret_cast<const float4 *>(ix->d_arena);
+    bp.row_chunks = g.row_floats / 4; bp.n = static_cast<uint32_t>(n); bp.m = g.m;
+    bp.cand = cand_dev; bp.K = K; bp.fw = d_fw.p; bp.adj = ix->d_adj;
+    const uint32_t cpl_raw = (bp.row_chunks + 31) / 32;
+    const int cpl = cpl_raw <= 1 ? 1 : cpl_raw <= 2 ? 2 : cpl_raw <= 4 ? 4 : cpl_raw <= 6 ? 6 : 8;
+    launch_build(g.metric, cpl, 1, bp, s); ix->launches++;
+    ZV_B(cudaGetLastError());
+    const uint64_t total = n * g.m;
+    const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((total + 255) / 256, 148ull * 16));
+    count_reverse_kernel<<<blocks, 256, 0, s>>>(d_fw.p, total, d_indeg.p); ix->launches++;
+    std::vector<uint32_t> indeg(n);
+    ZV_B(cudaMemcpyAsync(indeg.data(), d_indeg.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ZV_B(cudaStreamSynchronize(s));
+    std::vector<uint64_t> off(n + 1);
+    off[0] = 0;
+    for (uint64_t i = 0; i < n; ++i) off[i + 1] = off[i] + indeg[i];
+    ZV_B(d_rev.reserve(std::max<uint64_t>(off[n], 1)));
+    ZV_B(cudaMemcpyAsync(d_off.p, off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    fill_reverse_kernel<<<blocks, 256, 0, s>>>(d_fw.p, total, g.m, d_off.p, d_indeg.p + n, d_rev.p); ix->launches++;
+    bp.rev_off = d_off.p; bp.rev = d_rev.p;
+    launch_build(g.metric, cpl, 3, bp, s); ix->launches++;
+    ZV_B(cudaGetLastError());
+    ZV_B(cudaMemcpyAsync(g.adj0.data(), ix->d_adj, n * g.m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ZV_B(cudaStreamSynchronize(s));
+#undef ZV_B
+    cleanup();
+    g.rows_uploaded = n; g.dirty.clear(); g.adj_all_dirty = false;
+    ix->n_dev = n;
     return ZVDB_OK;
 }
 
@@ -462,10 +588,11 @@ int zvdb_sync_device(zvdb_index *ix) {
     return sync_device_locked(ix);
 }
 
-int zvdb_set_warps_per_query(zvdb_index *ix, uint32_t warps) {
+int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
-    if (warps > 8 || (warps & (warps - 1))) return fail(ZVDB_ERR_INVALID, "warps per query must be 0, 1, 2, 4 or 8");
-    ix->warps_per_query = warps;
+    const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u;
+    if (width > 2 || vis > 2 || variant > 15) return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap");
+    ix->variant = width; ix->visited_mode = vis;
     return ZVDB_OK;
 }
 

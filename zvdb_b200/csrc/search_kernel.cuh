@@ -1,4 +1,4 @@
-// search_kernel.cuh -- K1: batched layer-0 best-first search, one CTA ("team" of W warps) per query.
+// search_kernel.cuh -- K1: batched layer-0 best-first search, ONE WARP PER QUERY.
 //
 // Replaces the reference's search loop (src/hnsw.zig:201-224), its distance (:182-192) and the
 // result sort (:227-233), for nq queries at once:
@@ -14,13 +14,16 @@
 // What is ours:
 //   * candidate order is the strict total order (distance, id) -- the reference orders by distance
 //     only (:238-245) and lets its heap layout decide exact ties;
-//   * the unbounded heap is replaced by a sorted list that keeps only the best (ef - pops)
-//     candidates: at most that many more pops can happen, so nothing that could be popped is lost;
-//     dropped nodes stay in the visited set, as they would in the reference;
+//   * the unbounded binary heap is replaced by a sorted window plus a small unsorted "pending
+//     pool": pushes append to the pool, a pop takes min(window head, pool minimum), and the pool
+//     is merged into the window only when it fills up (one list shift per several pops). The
+//     window keeps only the best (ef - pops) keys: at most that many more pops can happen, so
+//     nothing that could still be popped is lost; dropped nodes stay visited, as in the reference;
 //   * the visited set is an exact open-addressing hash table in shared memory (never lossy);
-//   * distance is summed in lane order + xor butterfly (see row_distance), not sequentially: it
+//   * distance is summed in lane order + xor butterfly (see rows_distance), not sequentially: it
 //     differs from the reference by a few ulp (oracle mode ORC_DIST_TREE mirrors it bit for bit).
 //
+// One warp owns one query for its whole life: no CTA barriers, all hand-offs are __syncwarp().
 // Memory traffic per query (the HBM-gather roofline numerator):
 //   evals * row_bytes (row gathers) + pops * m * 4 (adjacency rows) + dim*4 (query) + k*12 (output).
 #pragma once
@@ -41,39 +44,60 @@ struct SearchParams {
     uint32_t row_chunks;     // float4 per arena row
     uint32_t m, n, entry, dim, nq, k, ef;
     uint32_t slots;          // visited-table slots (> max entries)
-    uint32_t hash_words;     // words reserved for the table (>= slots, >= 2*next_pow2(ef): reused by the final sort)
+    uint32_t hash_words;     // words reserved for the table (>= slots)
+    uint32_t cand_cap;       // entries reserved for the candidate window (>= ef, >= next_pow2(ef): reused by the final sort)
+    uint32_t *gbitmap;       // VIS_BITMAP: [gridDim.x][bm_words] visited bitmaps in global memory, all zero between queries
+    uint32_t *glog;          // VIS_BITMAP: [gridDim.x][log_cap] ids whose bit is set, so the bitmap can be wiped
+    uint32_t bm_words, log_cap;
 };
 
 enum : int { kMetricL2 = 0, kMetricCos = 1, kMetricDot = 2 };
+constexpr uint32_t kPoolCap = 64;   // pending pool slots
 
-// Rows a warp fetches before it starts reducing (loads in flight per lane = kUnroll * CPL float4).
-template <int CPL> struct Unroll { static constexpr int value = CPL <= 1 ? 8 : (CPL <= 2 ? 4 : 2); };
+// Rows a warp fetches before it starts reducing (loads in flight per lane = U * CPL float4).
+// WIDE is used when shared memory already limits residency to <= 16 warps per SM, so each thread
+// may hold twice the registers.
+template <int CPL, bool WIDE> struct Unroll {
+    static constexpr int narrow = CPL <= 1 ? 8 : (CPL <= 2 ? 4 : 2);
+    static constexpr int value = WIDE ? (CPL <= 4 ? narrow * 2 : narrow) : narrow;
+};
 
-// One lane's share of a row-vs-query distance. Lane l owns 16-byte chunks l, l+32, ... of the
-// row; inside a chunk x,y,z,w are accumulated in order with an UNFUSED multiply and add
-// (__fmul_rn/__fadd_rn stop ptxas from contracting to FFMA), mirroring the reference's
-// `diff*diff` then `sum +=` (hnsw.zig:188-189) element by element.
+// Packed f32x2 arithmetic (Blackwell FFMA2: PTX fma.rn.f32x2, sm_100+). A 16-byte chunk (x,y,z,w)
+// is two register pairs (x,y) and (z,w).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+
+struct Chunk2 { uint64_t xy, zw; };   // one 16-byte chunk as two packed pairs
+
+// One lane's share of a row-vs-query distance. Lane l owns 16-byte chunks l, l+32, ... of the row
+// and keeps TWO running sums: A0 takes elements x then z, A1 takes y then w, each by one fused
+// multiply-add per element (diff = q - v is a single rounding, as in hnsw.zig:188; the square and
+// the add are fused where the reference rounds twice, hnsw.zig:189 -- a few-ulp difference the
+// oracle's ORC_DIST_TREE mode restates exactly). The lane's partial sum is A0 + A1.
 template <int METRIC>
-__device__ __forceinline__ float accumulate_chunk(float acc, const float4 q, const float4 v) {
+__device__ __forceinline__ uint64_t accumulate_chunk(uint64_t acc, const Chunk2 q, const float4 v) {
+    const uint64_t vxy = pack2(v.x, v.y), vzw = pack2(v.z, v.w);
     if (METRIC == kMetricL2) {
-        float d;
-        d = __fsub_rn(q.x, v.x); acc = __fadd_rn(acc, __fmul_rn(d, d));
-        d = __fsub_rn(q.y, v.y); acc = __fadd_rn(acc, __fmul_rn(d, d));
-        d = __fsub_rn(q.z, v.z); acc = __fadd_rn(acc, __fmul_rn(d, d));
-        d = __fsub_rn(q.w, v.w); acc = __fadd_rn(acc, __fmul_rn(d, d));
+        const uint64_t neg1 = pack2(-1.0f, -1.0f);
+        const uint64_t dxy = ffma2(vxy, neg1, q.xy);       // q - v, one rounding
+        const uint64_t dzw = ffma2(vzw, neg1, q.zw);
+        acc = ffma2(dxy, dxy, acc);
+        acc = ffma2(dzw, dzw, acc);
     } else {
-        acc = __fadd_rn(acc, __fmul_rn(q.x, v.x));
-        acc = __fadd_rn(acc, __fmul_rn(q.y, v.y));
-        acc = __fadd_rn(acc, __fmul_rn(q.z, v.z));
-        acc = __fadd_rn(acc, __fmul_rn(q.w, v.w));
+        acc = ffma2(q.xy, vxy, acc);
+        acc = ffma2(q.zw, vzw, acc);
     }
     return acc;
 }
-
-__device__ __forceinline__ float warp_butterfly_sum(float acc) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(kFullMask, acc, off));
-    return acc;
+__device__ __forceinline__ float lane_partial(uint64_t acc) {
+    float a0, a1; unpack2(acc, a0, a1); return __fadd_rn(a0, a1);
 }
 
 template <int METRIC>
@@ -83,33 +107,84 @@ __device__ __forceinline__ float finish_distance(float s) {
     return s;
 }
 
-// Distances of up to U rows (ids[0..nrows)) to the query held in qv, by one warp. All the row
-// loads are issued before the first reduction so a warp keeps U*CPL 16-byte loads per lane in
-// flight. Every lane returns the same bits.
+// Transposed xor butterfly: reduces R per-lane partial sums (one per row) across the warp with
+// R/2 + R/4 + ... + 1 (+ log2(32/R)) shuffles instead of 5*R. At level `off` the lanes with bit
+// `off` clear keep the lower half of their rows and send the upper half, the others the reverse;
+// what a lane keeps is own + partner, exactly the operands (and, addition being commutative, the
+// bits) of the plain butterfly  acc += shfl_xor(acc, off)  for off = 16, 8, 4, 2, 1.
+// On return lane l holds the total of row l / (32 / R) in d[0].
+template <int R>
+__device__ __forceinline__ void transposed_reduce(float (&d)[R], uint32_t lane, int off) {
+    if constexpr (R == 1) {
+        for (; off >= 1; off >>= 1) d[0] = __fadd_rn(d[0], __shfl_xor_sync(kFullMask, d[0], off));
+    } else {
+        const bool upper = (lane & off) != 0;
+        float h[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) {
+            const float send = upper ? d[i] : d[i + R / 2];
+            const float keep = upper ? d[i + R / 2] : d[i];
+            h[i] = __fadd_rn(keep, __shfl_xor_sync(kFullMask, send, off));
+        }
+        transposed_reduce<R / 2>(h, lane, off >> 1);
+        d[0] = h[0];
+    }
+}
+
+// Distances of up to U rows (ids[0..nrows)) to the query held in qv, by one warp. All row loads
+// are issued before the first reduction: a warp keeps U*CPL 16-byte loads per lane in flight.
+// ids[u] for u >= nrows must still be valid row ids (callers pad with a hot row): a full-width
+// batch runs without per-row predicates. Returns, in every lane l, the distance of row l / (32/U)
+// (meaningless for rows >= nrows).
 template <int CPL, int METRIC, int U>
-__device__ __forceinline__ void rows_distance(const float4 *__restrict__ arena, uint32_t row_chunks,
-                                              const uint32_t (&ids)[U], int nrows, const float4 (&qv)[CPL],
-                                              int lane, float (&out)[U]) {
+__device__ __forceinline__ float rows_distance(const float4 *__restrict__ arena, uint32_t row_chunks,
+                                               const uint32_t (&ids)[U], const Chunk2 (&qv)[CPL], uint32_t lane) {
     float4 v[U][CPL];
+    const float4 *__restrict__ base = arena + lane;
+    if (row_chunks == 32u * CPL) {                       // every lane owns CPL chunks (dim a multiple of 128*CPL... the common case)
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+        for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const uint32_t chunk = lane + 32u * c;
-            v[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (u < nrows && chunk < row_chunks)
-                v[u][c] = __ldg(arena + static_cast<size_t>(ids[u]) * row_chunks + chunk);
+            for (int c = 0; c < CPL; ++c) v[u][c] = __ldg(base + static_cast<size_t>(ids[u]) * row_chunks + 32 * c);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                v[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane + 32u * c < row_chunks) v[u][c] = __ldg(base + static_cast<size_t>(ids[u]) * row_chunks + 32 * c);
+            }
         }
     }
+    float acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        float acc = 0.0f;
+        uint64_t a2 = 0;                                 // (+0.0f, +0.0f)
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) acc = accumulate_chunk<METRIC>(acc, qv[c], v[u][c]);
-        out[u] = acc;
+        for (int c = 0; c < CPL; ++c) a2 = accumulate_chunk<METRIC>(a2, qv[c], v[u][c]);
+        acc[u] = lane_partial(a2);
     }
+    transposed_reduce<U>(acc, lane, 16);
+    return finish_distance<METRIC>(acc[0]);
+}
+
+// Distance of ONE row, every lane returns it (plain butterfly; same bits as rows_distance).
+template <int CPL, int METRIC>
+__device__ __forceinline__ float row_distance(const float4 *__restrict__ arena, uint32_t row_chunks, uint32_t id,
+                                              const Chunk2 (&qv)[CPL], uint32_t lane) {
+    uint64_t a2 = 0;
 #pragma unroll
-    for (int u = 0; u < U; ++u) out[u] = finish_distance<METRIC>(warp_butterfly_sum(out[u]));
+    for (int c = 0; c < CPL; ++c) {
+        const uint32_t chunk = lane + 32u * c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (chunk < row_chunks) v = __ldg(arena + static_cast<size_t>(id) * row_chunks + chunk);
+        a2 = accumulate_chunk<METRIC>(a2, qv[c], v);
+    }
+    float acc = lane_partial(a2);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(kFullMask, acc, off));
+    return finish_distance<METRIC>(acc);
 }
 
 // Exact visited set: open addressing, linear probing, multiplicative hash reduced with a
@@ -133,132 +208,217 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t *a, uint32_t 
     }
     return lo;
 }
+// Number of entries in non-decreasing a[0..n) that are <= x.
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t *a, uint32_t n, uint32_t x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
 
-template <int CPL, int METRIC>
-__global__ void __launch_bounds__(256, (CPL <= 2 ? 4 : 2))
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int off) {
+    const uint32_t lo = __shfl_xor_sync(kFullMask, static_cast<uint32_t>(v), off);
+    const uint32_t hi = __shfl_xor_sync(kFullMask, static_cast<uint32_t>(v >> 32), off);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// Merge the pending pool into the sorted candidate window win[0..ns) keeping the best `cap` keys.
+// Returns the new window length. Warp-cooperative; pool/rank are shared-memory scratch.
+__device__ __forceinline__ uint32_t merge_pool(uint64_t *win, uint32_t ns, uint32_t cap, uint64_t *pool, uint32_t npool,
+                                               uint32_t *rank_ex, uint32_t lane) {
+    for (uint32_t t = npool + lane; t < kPoolCap; t += 32) pool[t] = ~0ull;
+    bitonic_sort_u64(pool, kPoolCap);                       // pool ascending; re[] below is then non-decreasing
+    uint64_t key[2]; uint32_t pos[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t t = lane + 32u * r;
+        pos[r] = kInvalidId; key[r] = ~0ull;
+        if (t < npool) {
+            key[r] = pool[t];
+            const uint32_t re = lower_bound_u64(win, ns, key[r]);   // existing keys below it
+            rank_ex[t] = re;
+            if (re + t < cap) pos[r] = re + t;                      // its rank in the union; beyond cap it can never be popped
+        }
+    }
+    __syncwarp();
+    const uint32_t lo = rank_ex[0];                         // first window slot that moves (npool >= 1)
+    // window keys [lo, ns) move right by the number of pool keys below them, top chunk first
+    for (uint32_t hi = ns; hi > lo;) {
+        const uint32_t span = min(32u, hi - lo);
+        const bool active = lane < span;
+        const uint32_t i = hi - 1u - lane;
+        uint64_t e = 0; uint32_t s = 0;
+        if (active) { e = win[i]; s = upper_bound_u32(rank_ex, npool, i); }
+        __syncwarp();
+        if (active && i + s < cap) win[i + s] = e;
+        hi -= span;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) if (pos[r] != kInvalidId) win[pos[r]] = key[r];
+    __syncwarp();
+    return min(ns + npool, cap);
+}
+
+enum : int { kVisSmemHash = 0, kVisGlobalBitmap = 1 };
+
+// VIS selects the exact visited set:
+//   kVisSmemHash     open-addressing table in shared memory (small ef*m: everything on chip);
+//   kVisGlobalBitmap one bit per node in global memory, one atomicOr per neighbour (a single round
+//                    trip, no probing). Shared memory then holds only the candidate lists, so
+//                    residency stays high at large ef. The CTA is persistent, owns one bitmap and
+//                    wipes it after each query from its log of set ids.
+template <int CPL, int METRIC, bool WIDE, int VIS>
+__global__ void __launch_bounds__(32, (WIDE ? (CPL <= 2 ? 16 : 8) : (CPL <= 2 ? 32 : 16)))
 search_layer0_kernel(const SearchParams p) {
-    constexpr int U = Unroll<CPL>::value;
+    constexpr int U = Unroll<CPL, WIDE>::value;
+    constexpr uint32_t LPR = 32 / U;                            // lanes holding the same row after the reduce
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);   // [ef]: [0,np) popped in pop order, [np,np+nc) candidates ascending
-    uint64_t *newk = keys + p.ef;                              // [32] keys pushed by the current pop
-    uint32_t *table = reinterpret_cast<uint32_t *>(newk + 32); // [hash_words] visited set; scratch for the final sort
-    uint32_t *todo = table + p.hash_words;                     // [32] unvisited neighbour ids of the current pop
-    uint32_t *rank_ex = todo + 32;                             // [32] #existing candidates below each new key
-    uint32_t *misc = rank_ex + 32;                             // [0] = #new, [1] = first candidate slot that moves
+    uint64_t *res = reinterpret_cast<uint64_t *>(smem_raw);     // [ef] popped keys in pop order
+    uint64_t *cand = res + ((p.ef + 1u) & ~1u);                 // [cand_cap] sorted window lives in [h, h+ns); final-sort scratch (keeps todo 16-byte aligned)
+    uint64_t *pool = cand + p.cand_cap;                         // [kPoolCap] pending pushes, unsorted
+    uint32_t *todo = reinterpret_cast<uint32_t *>(pool + kPoolCap);   // [32] unvisited neighbour ids of the current pass (16-byte aligned)
+    uint32_t *rank_ex = todo + 32;                              // [kPoolCap] merge scratch
+    uint32_t *table = rank_ex + kPoolCap;                       // kVisSmemHash: [hash_words]
+    uint32_t *bitmap = VIS == kVisGlobalBitmap ? p.gbitmap + static_cast<size_t>(blockIdx.x) * p.bm_words : nullptr;
+    uint32_t *vlog = VIS == kVisGlobalBitmap ? p.glog + static_cast<size_t>(blockIdx.x) * p.log_cap : nullptr;
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, W = blockDim.x >> 5, T = blockDim.x;
-    const uint32_t q = blockIdx.x;
+    const uint32_t lane = threadIdx.x;
     const float4 *__restrict__ arena = p.arena;
+    const uint32_t pass_w = min(p.m, 32u);
 
-    // Query -> registers (every warp of the team holds the whole query, chunked like a row).
-    float4 qv[CPL];
+    for (uint32_t q = blockIdx.x; q < p.nq; q += gridDim.x) {   // persistent when gridDim.x < nq
+    // Query -> registers, chunked like an arena row, packed in pairs for the f32x2 pipe.
+    Chunk2 qv[CPL];
     {
         const float *qp = p.queries + static_cast<size_t>(q) * p.dim;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             const uint32_t i = (lane + 32u * c) * 4u;
-            qv[c].x = i + 0 < p.dim ? qp[i + 0] : 0.f;
-            qv[c].y = i + 1 < p.dim ? qp[i + 1] : 0.f;
-            qv[c].z = i + 2 < p.dim ? qp[i + 2] : 0.f;
-            qv[c].w = i + 3 < p.dim ? qp[i + 3] : 0.f;
+            const float x = i + 0 < p.dim ? qp[i + 0] : 0.f, y = i + 1 < p.dim ? qp[i + 1] : 0.f;
+            const float z = i + 2 < p.dim ? qp[i + 2] : 0.f, w = i + 3 < p.dim ? qp[i + 3] : 0.f;
+            qv[c].xy = pack2(x, y); qv[c].zw = pack2(z, w);
         }
     }
-    for (uint32_t i = tid; i < p.slots; i += T) table[i] = kInvalidId;
-    team_sync();
-
-    uint32_t np = 0, nc = 1, nev = 1;   // pops done, candidates held, distance evaluations
-    if (warp == 0) {                    // hnsw.zig:208-209: push the entry point, mark it visited
-        uint32_t ids[U]; float d[U];
-        ids[0] = p.entry;
-        rows_distance<CPL, METRIC, U>(arena, p.row_chunks, ids, 1, qv, lane, d);
-        if (lane == 0) { keys[0] = pack_key(d[0], p.entry); visited_insert(table, p.slots, p.entry); }
+    if (VIS == kVisSmemHash) {
+        for (uint32_t i = lane; i < p.slots; i += 32) table[i] = kInvalidId;
     }
-    team_sync();
+    __syncwarp();
 
-    while (nc > 0 && np < p.ef) {                              // hnsw.zig:211
-        const uint32_t cur = key_id(keys[np]);                 // the minimum: candidates are sorted (:212)
-        ++np; --nc;                                            // it is now result[np-1] in place (:214)
-        const uint32_t cap = p.ef - np;                        // only this many more pops can ever happen
-        uint64_t *cand = keys + np;
-        for (uint32_t base = 0; base < p.m; base += 32) {      // hnsw.zig:216, 32 neighbours per pass
-            if (warp == 0) {
-                const uint32_t nb = (base + lane < p.m) ? __ldg(p.adj + static_cast<size_t>(cur) * p.m + base + lane)
-                                                        : kInvalidId;
-                const bool fresh = (nb != kInvalidId) && visited_insert(table, p.slots, nb);   // :217, :221
-                const unsigned mask = __ballot_sync(kFullMask, fresh);
-                if (fresh) todo[__popc(mask & ((1u << lane) - 1u))] = nb;   // adjacency order kept
-                if (lane == 0) misc[0] = __popc(mask);
+    // hnsw.zig:208-209: push the entry point, mark it visited
+    uint32_t np = 0, h = 0, ns = 0, npool = 1, nev = 1;   // pops, window start, window length, pool fill, evaluations
+    {
+        const float d0 = row_distance<CPL, METRIC>(arena, p.row_chunks, p.entry, qv, lane);
+        if (lane == 0) {
+            pool[0] = pack_key(d0, p.entry);
+            if (VIS == kVisSmemHash) visited_insert(table, p.slots, p.entry);
+            else { atomicOr(bitmap + (p.entry >> 5), 1u << (p.entry & 31)); vlog[0] = p.entry; }
+        }
+    }
+    uint64_t worst = ~0ull;            // largest key of a FULL window: worse pushes can never be popped
+    // adjacency of the predicted next pop, fetched one iteration ahead
+    uint32_t pref_id = kInvalidId, pref_nb = kInvalidId;
+    __syncwarp();
+
+    while (np < p.ef) {                                          // hnsw.zig:211
+        // ---- pop (:212): min(window head, pool minimum) ----
+        uint64_t pk = ~0ull;
+        if (lane < npool) pk = pool[lane];
+        if (lane + 32 < npool) pk = min(pk, pool[lane + 32]);
+        uint64_t pmin = pk;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) pmin = min(pmin, shfl_xor_u64(pmin, off));
+        const uint64_t head = ns > 0 ? cand[h] : ~0ull;
+        const uint64_t cur_key = min(head, pmin);
+        if (cur_key == ~0ull) break;                             // candidates.count() == 0
+        if (head <= pmin) { ++h; --ns; }
+        else {
+            // remove it from the pool: the last entry takes its slot
+            const uint32_t owner = __ffs(__ballot_sync(kFullMask, pk == pmin)) - 1;
+            uint32_t slot = (lane < npool && pool[lane] == pmin) ? lane : lane + 32;
+            slot = __shfl_sync(kFullMask, slot, owner);
+            __syncwarp();
+            if (lane == 0) pool[slot] = pool[npool - 1];
+            --npool;
+        }
+        if (lane == 0) res[np] = cur_key;                        // :214
+        ++np;
+        const uint32_t cur = key_id(cur_key);
+        const uint32_t cap = p.ef - np;                          // only this many more pops can ever happen
+        if (ns > cap) { ns = cap; }                              // the window tail can no longer be reached
+        if (ns < cap) worst = ~0ull;
+        __syncwarp();
+
+        for (uint32_t base = 0; base < p.m; base += 32) {        // :216, 32 neighbours per pass
+            if (npool + pass_w > kPoolCap) {                     // make room for this pass's pushes
+                ns = merge_pool(cand + h, ns, cap, pool, npool, rank_ex, lane);
+                npool = 0;
+                worst = (ns == cap && ns > 0) ? cand[h + ns - 1] : ~0ull;
             }
-            team_sync();
-            const uint32_t t = misc[0];
-            if (t == 0) { team_sync(); continue; }
+            uint32_t nb;
+            if (base == 0 && cur == pref_id) nb = pref_nb;
+            else nb = (base + lane < p.m) ? __ldg(p.adj + static_cast<size_t>(cur) * p.m + base + lane) : kInvalidId;
+            if (base == 0) {
+                // predicted next pop = new window head (pushes of this pop may still beat it)
+                pref_id = ns > 0 ? key_id(cand[h]) : kInvalidId;
+                pref_nb = (pref_id != kInvalidId && lane < p.m) ? __ldg(p.adj + static_cast<size_t>(pref_id) * p.m + lane) : kInvalidId;
+            }
+            bool fresh = false;                                  // :217, :221
+            if (nb != kInvalidId) {
+                if (VIS == kVisSmemHash) fresh = visited_insert(table, p.slots, nb);
+                else fresh = ((atomicOr(bitmap + (nb >> 5), 1u << (nb & 31)) >> (nb & 31)) & 1u) == 0;
+            }
+            const unsigned mask = __ballot_sync(kFullMask, fresh);
+            const uint32_t t = __popc(mask);
+            if (t == 0) continue;
+            const uint32_t slot_t = __popc(mask & ((1u << lane) - 1u));
+            if (fresh) todo[slot_t] = nb;                        // adjacency order kept
+            else if (lane - slot_t + t < 32u) todo[lane - slot_t + t] = cur;   // pad todo[t..32) with a hot, valid row id
+            if (VIS == kVisGlobalBitmap) { if (fresh) vlog[nev + slot_t] = nb; }
             nev += t;
+            __syncwarp();
 
-            // ---- distances (:219): warp w takes rows w, w+W, ... U at a time ----
-            for (uint32_t j0 = warp * U; j0 < t; j0 += W * U) {
-                uint32_t ids[U]; float d[U];
+            // ---- distances (:219) and push (:220) into the pending pool ----
+            for (uint32_t j0 = 0; j0 < t; j0 += U) {
+                uint32_t ids[U];
                 const int nrows = min(static_cast<int>(t - j0), U);
+                if constexpr (U >= 4) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) ids[u] = (u < nrows) ? todo[j0 + u] : 0u;
-                rows_distance<CPL, METRIC, U>(arena, p.row_chunks, ids, nrows, qv, lane, d);
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (static_cast<int>(lane) == u && u < nrows) newk[j0 + u] = pack_key(d[u], ids[u]);
-            }
-            team_sync();
-
-            // ---- push (:220) = merge the t new keys into the sorted candidates, keep the best `cap` ----
-            uint32_t my_pos = kInvalidId; uint64_t my_key = 0;
-            if (warp == 0) {
-                uint32_t lo_mine = kInvalidId;
-                if (lane < t) {
-                    my_key = newk[lane];
-                    const uint32_t re = lower_bound_u64(cand, nc, my_key);
-                    uint32_t rn = 0;
-                    for (uint32_t l = 0; l < t; ++l) rn += (newk[l] < my_key) ? 1u : 0u;
-                    rank_ex[lane] = re;
-                    if (re + rn < cap) { my_pos = re + rn; lo_mine = re; }
-                }
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) lo_mine = min(lo_mine, __shfl_xor_sync(kFullMask, lo_mine, off));
-                if (lane == 0) misc[1] = lo_mine;
-            }
-            team_sync();
-            const uint32_t lo = misc[1];
-            if (lo != kInvalidId) {
-                // candidates [lo, nc) move right by the number of new keys below them, top chunk first
-                for (uint32_t hi = nc; hi > lo;) {
-                    const uint32_t span = min(T, hi - lo);
-                    const bool active = tid < span;
-                    const uint32_t i = hi - 1u - tid;
-                    uint64_t e = 0; uint32_t s = 0;
-                    if (active) {
-                        e = cand[i];
-                        for (uint32_t l = 0; l < t; ++l) s += (rank_ex[l] <= i) ? 1u : 0u;
+                    for (int u = 0; u < U; u += 4) {
+                        const uint4 w = *reinterpret_cast<const uint4 *>(todo + j0 + u);
+                        ids[u] = w.x; ids[u + 1] = w.y; ids[u + 2] = w.z; ids[u + 3] = w.w;
                     }
-                    team_sync();
-                    if (active && i + s < cap) cand[i + s] = e;
-                    hi -= span;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) ids[u] = todo[j0 + u];
                 }
-                team_sync();
-                if (my_pos != kInvalidId) cand[my_pos] = my_key;
+                const float d = rows_distance<CPL, METRIC, U>(arena, p.row_chunks, ids, qv, lane);
+                const uint32_t r = lane / LPR;                   // the row this lane holds
+                uint64_t key = ~0ull;
+                if ((lane % LPR) == 0 && r < static_cast<uint32_t>(nrows)) key = pack_key(d, todo[j0 + r]);
+                const bool keep = key < worst;                   // false for idle lanes too (key = ~0)
+                const unsigned km = __ballot_sync(kFullMask, keep);
+                if (keep) pool[npool + __popc(km & ((1u << lane) - 1u))] = key;
+                npool += __popc(km);
             }
-            nc = min(nc + t, cap);
-            team_sync();
+            __syncwarp();
         }
     }
 
     // ---- result: stable sort of the popped entries by distance over pop order (hnsw.zig:227-233) ----
-    uint64_t *sorted = reinterpret_cast<uint64_t *>(table);
+    __syncwarp();
+    uint64_t *sorted = cand;                                     // the window is dead now
     const uint32_t p2 = next_pow2(np);
-    for (uint32_t i = tid; i < p2; i += T)
-        sorted[i] = i < np ? ((keys[i] & 0xFFFFFFFF00000000ull) | i) : ~0ull;
+    for (uint32_t i = lane; i < p2; i += 32)
+        sorted[i] = i < np ? ((res[i] & 0xFFFFFFFF00000000ull) | i) : ~0ull;
     bitonic_sort_u64(sorted, p2);
     const uint32_t nres = min(np, p.k);
-    for (uint32_t r = tid; r < p.k; r += T) {
+    for (uint32_t r = lane; r < p.k; r += 32) {
         const size_t o = static_cast<size_t>(q) * p.k + r;
         if (r < nres) {
-            const uint64_t key = keys[static_cast<uint32_t>(sorted[r])];
+            const uint64_t key = res[static_cast<uint32_t>(sorted[r])];
             p.ids[o] = static_cast<uint64_t>(key_id(key)) * p.id_stride + p.id_base;
             p.dist[o] = key_dist(key);
         } else {
@@ -266,11 +426,18 @@ search_layer0_kernel(const SearchParams p) {
             p.dist[o] = 0.0f;
         }
     }
-    if (tid == 0) {
+    if (lane == 0) {
         p.counts[q] = nres;
         if (p.pops) p.pops[q] = np;
         if (p.evals) p.evals[q] = nev;
     }
+    if (VIS == kVisGlobalBitmap) {       // wipe exactly the words this query set, then order the wipe before the next query's atomics
+        __syncwarp();
+        for (uint32_t i = lane; i < nev; i += 32) bitmap[vlog[i] >> 5] = 0u;
+        __threadfence();
+    }
+    __syncwarp();
+    }   // persistent query loop
 }
 
 }  // namespace zvdb

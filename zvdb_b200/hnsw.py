@@ -167,6 +167,18 @@ class HNSW:
         np.cumsum(deg, out=off[1:])
         self.load_graph(points, off, adj[valid], entry)
 
+    def build_from_candidates(self, points, cand=None, K: int = 0, cand_device_ptr: int = 0) -> None:
+        """Replace the index by a graph built on the GPU from candidate lists (builder.cuh).
+        `cand`: host array [n, K] of uint32 ids, or pass cand_device_ptr + K for a device array."""
+        p = np.ascontiguousarray(points, np.float32)
+        if cand_device_ptr:
+            L.check(L.lib().zvdb_build_from_candidates(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.shape[0],
+                                                       p.shape[1], cand_device_ptr, K, 1))
+        else:
+            c = np.ascontiguousarray(cand, np.uint32)
+            L.check(L.lib().zvdb_build_from_candidates(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.shape[0],
+                                                       p.shape[1], c.ctypes.data, c.shape[1], 0))
+
     # -- search (hnsw.zig:194) -------------------------------------------------------------------
     def search(self, query: Sequence[float], k: int) -> list:
         """`search(query, k)`: list of Node, len = min(k, reachable); empty index -> []."""
@@ -217,8 +229,8 @@ class HNSW:
     def sync_device(self) -> None:
         L.check(L.lib().zvdb_sync_device(self._h))
 
-    def set_warps_per_query(self, warps: int) -> None:
-        L.check(L.lib().zvdb_set_warps_per_query(self._h, warps))
+    def set_kernel_variant(self, variant: int) -> None:
+        L.check(L.lib().zvdb_set_kernel_variant(self._h, variant))
 
     def kernel_launches(self) -> int:
         return int(L.lib().zvdb_kernel_launches(self._h))

@@ -55,6 +55,7 @@ def parse_args():
     p.add_argument("--sweep", action="store_true", help="also report the ef sweep 32..512 (untimed extra passes)")
     p.add_argument("--variant", type=int, default=0, help="search kernel variant: 0 auto, 1 narrow, 2 wide")
     p.add_argument("--cpu-sample", type=int, default=2000, help="queries in the CPU-baseline sample")
+    p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return p.parse_args()
 
 
@@ -357,7 +358,7 @@ def run_ours(args):
 
     # ---- CPU baseline: the oracle on the host cores, bounded sample of the same workload ---------
     cpu = None
-    if world == 1:
+    if world == 1 and not args.no_cpu:
         from oracle import oracle as O
         O.build()
         adj, _ = h.export_layer(0)

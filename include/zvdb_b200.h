@@ -157,6 +157,22 @@ ZVDB_API int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant);
 /* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */
 ZVDB_API uint64_t zvdb_kernel_launches(const zvdb_index *ix);
 
+/* ---- exact brute-force k-NN (north_star subsystem 3; no reference counterpart) ---------------- */
+
+/* Exact k nearest rows of every query under the index metric, for ground truth and re-rank:
+ * a 3xTF32 tcgen05 GEMM fused with a per-thread top-k (zvdb_b200/csrc/bruteforce.cuh), then an
+ * exact fp32 re-rank, so the returned distances are bit-identical to what zvdb_search_batch
+ * returns for the same (query, id). Order: (distance, id). HOST buffers: queries[nq x dim] in,
+ * ids[nq x k], dist[nq x k], counts[nq] (= min(k, count)) out. k <= 1024. */
+ZVDB_API int zvdb_bruteforce_knn(zvdb_index *ix, const float *queries, uint64_t nq, uint32_t dim, uint32_t k,
+                                 uint64_t *ids, float *dist, uint32_t *counts);
+
+/* Same with DEVICE buffers, enqueued on `stream` without synchronising; ids are written as
+ * id * id_stride + id_base (see zvdb_search_batch_device). */
+ZVDB_API int zvdb_bruteforce_knn_device(zvdb_index *ix, const float *d_queries, uint64_t nq, uint32_t k,
+                                        uint64_t *d_ids, float *d_dist, uint32_t *d_counts, uint64_t id_stride,
+                                        uint64_t id_base, void *stream);
+
 /* ---- shard merge --------------------------------------------------------------- */
 
 /* k-way merge of G per-shard result sets gathered as d_dist/d_ids [G][nq][k], d_counts [G][nq]

@@ -38,6 +38,8 @@ SIGNATURES = {
     "zvdb_search": (_i32, [_vp, _pf, _u32, _u32, _pu64, _pf, _pu32]),
     "zvdb_search_batch": (_i32, [_vp, _vp, _u64, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "zvdb_search_batch_device": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp]),
+    "zvdb_bruteforce_knn": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp]),
+    "zvdb_bruteforce_knn_device": (_i32, [_vp, _vp, _u64, _u32, _vp, _vp, _vp, _u64, _u64, _vp]),
     "zvdb_sync_device": (_i32, [_vp]),
     "zvdb_set_kernel_variant": (_i32, [_vp, _u32]),
     "zvdb_kernel_launches": (_u64, [_vp]),

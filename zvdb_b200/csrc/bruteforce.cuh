@@ -1,0 +1,390 @@
+// bruteforce.cuh -- K4: exact brute-force k-NN on the 5th-generation tensor cores (north_star
+// subsystem 3). No reference counterpart: zvdb has no exact search.
+// It provides ground truth for recall and a re-rank path, behind zvdb_bruteforce_knn*().
+//
+//   scores  S[q][r] = dot(Q[q], X[r])                    one GEMM, nq x n x dim
+//   L2:     d = |x_r|^2 - 2 S   (|q|^2 is constant per query and dropped for ranking)
+//   cosine: d = -S  (rows are normalised at insert);  dot: d = -S
+//
+// fp32-faithful products on TF32 tensor cores (3xTF32): every operand is split on the device into
+// hi = x with the low 13 mantissa bits cleared and lo = (x - hi) with its low 13 bits cleared, both
+// exactly representable in TF32, and  S = lo*hi + hi*lo + hi*hi  is accumulated in fp32 in TMEM
+// (the dropped lo*lo term is below 2^-22 relative). Because the operands carry no bits the tensor
+// core would discard, the result does not depend on whether the hardware truncates or rounds.
+//
+// Kernel structure (one persistent CTA per SM, 192 threads, sm_100a only):
+//   warp 0   TMA producer : cp.async.bulk.tensor (128B swizzle) of Q_hi, Q_lo, X_hi, X_lo K-chunks
+//                           into a multi-stage shared-memory ring, mbarrier complete_tx
+//   warp 1   MMA issuer   : one thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128 (queries)
+//                           x N=128 (rows) x K=8, accumulators in TMEM, double buffered (2 x 128
+//                           columns); tcgen05.commit releases smem stages / publishes accumulators
+//   warps 2-5 epilogue    : tcgen05.ld 32x32b of the accumulator (thread t owns query t of the
+//                           tile = TMEM lane t), distance formed in registers, threshold filter
+//                           against the thread's running k-th best, rare insertion into a sorted
+//                           per-thread list (shared memory; global memory when k is large).
+//                           The score matrix never exists in memory.
+// A work item is (query tile, row split); each item leaves a sorted candidate list per query. A
+// second small kernel merges the splits, RE-COMPUTES the distance of the best k+slack candidates
+// exactly (difference form, the same summation order as the search kernel, so both kernels return
+// bit-identical distances for the same (query, id)), orders by (distance, id) and writes k.
+#pragma once
+#include <cuda.h>
+#include "search_kernel.cuh"
+
+namespace zvdb {
+namespace bf {
+
+constexpr uint32_t kBM = 128;                        // queries per tile (UMMA M)
+constexpr uint32_t kBN = 128;                        // rows per tile    (UMMA N)
+constexpr uint32_t kBK = 32;                         // floats per K chunk = 128 bytes = one swizzle row
+constexpr uint32_t kUmmaK = 8;                       // K of one tcgen05.mma.kind::tf32
+constexpr uint32_t kTileBytes = kBM * kBK * 4;       // 16 KiB
+constexpr uint32_t kStageBytes = 4 * kTileBytes;     // Q_hi, Q_lo, X_hi, X_lo
+constexpr uint32_t kThreads = 192;
+constexpr uint32_t kTmemCols = 2 * kBN;              // two accumulator buffers
+constexpr uint32_t kSlack = 8;                       // candidates kept beyond k for the exact re-rank
+constexpr uint32_t kMaxStages = 3;
+
+struct BfParams {
+    const float *xnorm;      // [n] squared row norms (L2 only)
+    uint64_t *part_keys;     // [n_splits][nq][kp] sorted candidate keys per (split, query)
+    uint64_t *glists;        // [gridDim.x][kp][128] per-thread lists when they do not fit in smem, else null
+    uint32_t n, nq, kchunks, kp;
+    uint32_t n_qtiles, n_splits, tiles_per_split, n_rtiles, stages, metric;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane.
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor of a [128 rows][32 floats] K-major tile written by TMA with the
+// 128-byte swizzle: rows are 128 bytes, 8-row groups are 1024 bytes apart (SBO), LBO is unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);     // start address, 16-byte units
+    d |= static_cast<uint64_t>(1) << 16;                     // leading byte offset (ignored for swizzled K-major)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride byte offset
+    d |= static_cast<uint64_t>(1) << 46;                     // descriptor version of sm_100
+    d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = 128.
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kBN >> 3) << 17) | ((kBM >> 4) << 24);
+
+// Sorted insertion into this thread's candidate list (ascending keys, stride 128 entries between
+// positions so the 128 epilogue threads interleave). Returns the new threshold distance.
+__device__ __noinline__ float list_insert(uint64_t *L, uint32_t kp, uint64_t key) {
+    uint32_t pos = kp - 1;
+    while (pos > 0) {
+        const uint64_t prev = L[static_cast<size_t>(pos - 1) * 128];
+        if (prev <= key) break;
+        L[static_cast<size_t>(pos) * 128] = prev;
+        --pos;
+    }
+    L[static_cast<size_t>(pos) * 128] = key;
+    const uint64_t worst = L[static_cast<size_t>(kp - 1) * 128];
+    return worst == ~0ull ? __int_as_float(0x7f800000) : key_dist(worst);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
+                    const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+                    const BfParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled TMA tiles want a 1024-byte aligned base
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + static_cast<size_t>(p.stages) * kStageBytes);
+    uint64_t *full = bars, *empty = bars + kMaxStages, *tfull = bars + 2 * kMaxStages, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+    float *xn_s = reinterpret_cast<float *>(bars + 16);                           // [2][128], 16-byte aligned (read as float4)
+    uint64_t *lists_s = reinterpret_cast<uint64_t *>(xn_s + 2 * kBN);             // [kp][128] when in smem
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (uint32_t b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t n_items = p.n_qtiles * p.n_splits;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const uint32_t split = item / p.n_qtiles, qt = item % p.n_qtiles;
+                const uint32_t t0 = split * p.tiles_per_split, t1 = min(p.n_rtiles, t0 + p.tiles_per_split);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    for (uint32_t kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(empty + stage, phase ^ 1);
+                        mbar_expect_tx(full + stage, kStageBytes);
+                        uint8_t *st = tiles + static_cast<size_t>(stage) * kStageBytes;
+                        const int32_t kx = static_cast<int32_t>(kc * kBK);
+                        tma_load_2d(st, &tm_qhi, full + stage, kx, static_cast<int32_t>(qt * kBM));
+                        tma_load_2d(st + kTileBytes, &tm_qlo, full + stage, kx, static_cast<int32_t>(qt * kBM));
+                        tma_load_2d(st + 2 * kTileBytes, &tm_xhi, full + stage, kx, static_cast<int32_t>(t * kBN));
+                        tma_load_2d(st + 3 * kTileBytes, &tm_xlo, full + stage, kx, static_cast<int32_t>(t * kBN));
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, tile_count = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const uint32_t split = item / p.n_qtiles;
+                const uint32_t t0 = split * p.tiles_per_split, t1 = min(p.n_rtiles, t0 + p.tiles_per_split);
+                for (uint32_t t = t0; t < t1; ++t, ++tile_count) {
+                    const uint32_t buf = tile_count & 1, use = tile_count >> 1;
+                    mbar_wait(tempty + buf, (use & 1) ^ 1);          // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * kBN;
+                    for (uint32_t kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(tiles + static_cast<size_t>(stage) * kStageBytes);
+                        const uint64_t q_hi = make_smem_desc(sa), q_lo = make_smem_desc(sa + kTileBytes);
+                        const uint64_t x_hi = make_smem_desc(sa + 2 * kTileBytes), x_lo = make_smem_desc(sa + 3 * kTileBytes);
+#pragma unroll
+                        for (uint32_t ks = 0; ks < kBK / kUmmaK; ++ks) {
+                            const uint64_t off = (ks * kUmmaK * 4) >> 4;     // 32 bytes per K step, in 16-byte units
+                            tc_mma_tf32(d_tmem, q_lo + off, x_hi + off, kInstrDesc, (kc | ks) != 0);   // small terms first
+                            tc_mma_tf32(d_tmem, q_hi + off, x_lo + off, kInstrDesc, 1);
+                            tc_mma_tf32(d_tmem, q_hi + off, x_hi + off, kInstrDesc, 1);
+                        }
+                        tc_commit(empty + stage);                    // stage reusable once these MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(tfull + buf);                          // accumulator complete
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, thread = one query of the tile = one TMEM lane =====
+        const uint32_t wq = warp & 3;                                // TMEM lane quarter this warp may read
+        const uint32_t et = wq * 32 + lane;                          // query row in the tile
+        uint64_t *L = p.glists ? p.glists + static_cast<size_t>(blockIdx.x) * p.kp * 128 + et : lists_s + et;
+        const float scale = p.metric == kMetricL2 ? -2.0f : -1.0f;
+        const float inf = __int_as_float(0x7f800000);
+        uint32_t tile_count = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const uint32_t split = item / p.n_qtiles, qt = item % p.n_qtiles;
+            const uint32_t t0 = split * p.tiles_per_split, t1 = min(p.n_rtiles, t0 + p.tiles_per_split);
+            for (uint32_t i = 0; i < p.kp; ++i) L[static_cast<size_t>(i) * 128] = ~0ull;
+            float tau = inf;
+            for (uint32_t t = t0; t < t1; ++t, ++tile_count) {
+                const uint32_t buf = tile_count & 1, use = tile_count >> 1;
+                const uint32_t row0 = t * kBN;
+                {
+                    const uint32_t r = row0 + et;
+                    xn_s[buf * kBN + et] = r < p.n ? (p.metric == kMetricL2 ? __ldg(p.xnorm + r) : 0.0f) : inf;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");       // the 128 epilogue threads only
+                mbar_wait(tfull + buf, use & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((wq * 32u) << 16) + buf * kBN;
+#pragma unroll 1
+                for (uint32_t c = 0; c < kBN / 32; ++c) {
+                    uint32_t acc[32];
+                    tc_ld32(taddr + c * 32, acc);
+                    const float4 *xn4 = reinterpret_cast<const float4 *>(xn_s + buf * kBN + c * 32);
+                    float d[32];
+                    float mn = inf;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 x = xn4[j];
+                        d[4 * j + 0] = fmaf(scale, __uint_as_float(acc[4 * j + 0]), x.x);
+                        d[4 * j + 1] = fmaf(scale, __uint_as_float(acc[4 * j + 1]), x.y);
+                        d[4 * j + 2] = fmaf(scale, __uint_as_float(acc[4 * j + 2]), x.z);
+                        d[4 * j + 3] = fmaf(scale, __uint_as_float(acc[4 * j + 3]), x.w);
+                        mn = fminf(mn, fminf(fminf(d[4 * j + 0], d[4 * j + 1]), fminf(d[4 * j + 2], d[4 * j + 3])));
+                    }
+                    if (mn < tau) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            // rows arrive in ascending id order, so on an exact tie the earlier id stays: strict <
+                            if (d[j] < tau) tau = list_insert(L, p.kp, pack_key(d[j], row0 + c * 32 + j));
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + buf);
+            }
+            const uint32_t q = qt * kBM + et;
+            if (q < p.nq) {
+                uint64_t *out = p.part_keys + (static_cast<size_t>(split) * p.nq + q) * p.kp;
+                for (uint32_t i = 0; i < p.kp; ++i) out[i] = L[static_cast<size_t>(i) * 128];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- operand split ----------------------------------------------------------------------------
+// One warp per row: hi/lo TF32 parts into [rows][dst_pitch] (zero padded beyond `cols`), and the
+// squared norm of the row (fp32, lane order + butterfly) when `norm` is given.
+__global__ void split_tf32_kernel(const float *__restrict__ src, uint32_t src_pitch, uint32_t cols, uint64_t rows,
+                                  float *__restrict__ hi, float *__restrict__ lo, uint32_t dst_pitch, float *__restrict__ norm) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t r = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+        float acc = 0.0f;
+        for (uint32_t c = lane; c < dst_pitch; c += 32) {
+            const float x = c < cols ? src[r * src_pitch + c] : 0.0f;
+            const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            const float l = __uint_as_float(__float_as_uint(__fsub_rn(x, h)) & 0xFFFFE000u);
+            hi[r * dst_pitch + c] = h;
+            lo[r * dst_pitch + c] = l;
+            acc = fmaf(x, x, acc);
+        }
+        if (norm) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(kFullMask, acc, off);
+            if (lane == 0) norm[r] = acc;
+        }
+    }
+}
+
+// ---- merge of the splits + exact re-rank ---------------------------------------------------------
+struct BfFinalParams {
+    const float4 *arena;
+    const float *queries;      // [nq][dim]
+    const uint64_t *part_keys; // [n_splits][nq][kp]
+    uint64_t *ids;             // [nq][k]
+    float *dist;               // [nq][k]
+    uint32_t *counts;          // [nq]
+    uint64_t id_stride, id_base;
+    uint32_t row_chunks, dim, nq, k, kp, n_splits, p2, kk2;   // p2 = pow2 >= n_splits*kp ; kk2 = pow2 >= k + kSlack
+};
+
+template <int CPL, int METRIC>
+__global__ void __launch_bounds__(32) bf_finalize_kernel(const BfFinalParams p) {
+    constexpr int U = Unroll<CPL, false>::value;
+    constexpr uint32_t LPR = 32 / U;
+    extern __shared__ __align__(16) unsigned char smem_fin[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_fin);      // [p2]
+    uint64_t *exact = keys + p.p2;                                // [kk2]
+    const uint32_t q = blockIdx.x, lane = threadIdx.x;
+    const uint32_t total = p.n_splits * p.kp;
+    for (uint32_t i = lane; i < p.p2; i += 32) {
+        uint64_t key = ~0ull;
+        if (i < total) key = p.part_keys[(static_cast<size_t>(i / p.kp) * p.nq + q) * p.kp + (i % p.kp)];
+        keys[i] = key;
+    }
+    bitonic_sort_u64(keys, p.p2);
+    const uint32_t want = min(p.k + kSlack, total);
+    Chunk2 qv[CPL];
+    {
+        const float *qp = p.queries + static_cast<size_t>(q) * p.dim;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const uint32_t i = (lane + 32u * c) * 4u;
+            const float x = i + 0 < p.dim ? qp[i + 0] : 0.f, y = i + 1 < p.dim ? qp[i + 1] : 0.f;
+            const float z = i + 2 < p.dim ? qp[i + 2] : 0.f, w = i + 3 < p.dim ? qp[i + 3] : 0.f;
+            qv[c].xy = pack2(x, y); qv[c].zw = pack2(z, w);
+        }
+    }
+    for (uint32_t i = lane; i < p.kk2; i += 32) exact[i] = ~0ull;
+    __syncwarp();
+    uint32_t nvalid = 0;
+    for (uint32_t j0 = 0; j0 < want; j0 += U) {
+        uint32_t ids[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t key = j0 + u < want ? keys[j0 + u] : ~0ull;
+            ok[u] = key != ~0ull;
+            ids[u] = ok[u] ? key_id(key) : 0u;                   // row 0 always exists when any key is valid
+        }
+        const float d = rows_distance<CPL, METRIC, U>(p.arena, p.row_chunks, ids, qv, lane);
+        const uint32_t r = lane / LPR;
+        bool mine = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (r == static_cast<uint32_t>(u)) mine = ok[u];
+        if ((lane % LPR) == 0 && mine) {
+            uint32_t id = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (r == static_cast<uint32_t>(u)) id = ids[u];
+            exact[j0 + r] = pack_key(d, id);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) nvalid += ok[u] ? 1u : 0u;
+    }
+    __syncwarp();
+    bitonic_sort_u64(exact, p.kk2);
+    const uint32_t nres = min(nvalid, p.k);
+    for (uint32_t r = lane; r < p.k; r += 32) {
+        const size_t o = static_cast<size_t>(q) * p.k + r;
+        if (r < nres) {
+            p.ids[o] = static_cast<uint64_t>(key_id(exact[r])) * p.id_stride + p.id_base;
+            p.dist[o] = key_dist(exact[r]);
+        } else {
+            p.ids[o] = ~0ull;
+            p.dist[o] = 0.0f;
+        }
+    }
+    if (lane == 0) p.counts[q] = nres;
+}
+
+}  // namespace bf
+}  // namespace zvdb

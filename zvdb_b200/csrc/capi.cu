@@ -13,6 +13,7 @@
 #include "host_graph.hpp"
 #include "search_kernel.cuh"
 #include "builder.cuh"
+#include "bruteforce.cuh"
 
 namespace zvdb {
 
@@ -78,6 +79,10 @@ struct zvdb_index {
     DevBuf<float> q_buf, dist_buf;
     DevBuf<uint64_t> ids_buf;
     DevBuf<uint32_t> cnt_buf, pops_buf, evals_buf, scat_rows, scat_ids, bitmap_buf, vlog_buf;
+    // K4 (brute force): TF32 hi/lo split of the arena + squared row norms, rebuilt when the rows change
+    DevBuf<float> bf_xhi, bf_xlo, bf_xnorm, bf_qhi, bf_qlo;
+    DevBuf<uint64_t> bf_part, bf_glists;
+    uint64_t bf_rows = 0;           // rows covered by bf_xhi/bf_xlo (0 = stale)
     uint32_t variant = 0;           // 0 automatic, 1 narrow, 2 wide (tuning/testing)
     uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap
     std::atomic<uint64_t> launches{0};
@@ -141,6 +146,7 @@ static int sync_device_locked(zvdb_index *ix) {
         ZV_CUDA(cudaStreamSynchronize(ix->stream));   // `rows` is stack-owned pageable memory
     }
     ZV_CUDA(cudaStreamSynchronize(ix->stream));
+    if (g.rows_uploaded != g.n) ix->bf_rows = 0;   // the brute-force operand split no longer covers every row
     g.rows_uploaded = g.n; g.dirty.clear(); g.adj_all_dirty = false;
     ix->n_dev = g.n;
     return ZVDB_OK;
@@ -323,6 +329,153 @@ static void launch_build(int metric, int cpl, int stage, const BuildParams &bp, 
     else launch_build_metric<kMetricDot>(cpl, stage, bp, s);
 }
 
+// ---- K4 launch: exact brute-force k-NN ----------------------------------------------------------
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// [rows][pitch floats] fp32, K contiguous; box = 32 floats x 128 rows, 128-byte swizzle, zero fill out of bounds.
+static int make_tile_map(CUtensorMap *map, const float *base, uint64_t rows, uint32_t pitch_floats) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return fail(ZVDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {pitch_floats, rows};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_floats) * sizeof(float)};
+    const cuuint32_t box[2] = {bf::kBK, bf::kBN};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ZVDB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ")");
+    return ZVDB_OK;
+}
+
+template <int METRIC>
+static cudaError_t launch_bf_final_metric(int cpl, const bf::BfFinalParams &fp, size_t smem, cudaStream_t s) {
+#define ZV_FIN(C)                                                                                            \
+    case C: {                                                                                                \
+        auto kern = bf::bf_finalize_kernel<C, METRIC>;                                                       \
+        if (smem > 48 * 1024) {                                                                              \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+            if (e != cudaSuccess) return e;                                                                  \
+        }                                                                                                    \
+        kern<<<fp.nq, 32, smem, s>>>(fp);                                                                    \
+        return cudaGetLastError();                                                                           \
+    }
+    switch (cpl) { ZV_FIN(1) ZV_FIN(2) ZV_FIN(4) ZV_FIN(6) ZV_FIN(8) }
+#undef ZV_FIN
+    return cudaErrorInvalidValue;
+}
+
+// Device queries in, device results out, enqueued on `s`. Caller holds the lock; the device copy is current.
+static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t k, uint64_t *d_ids, float *d_dist,
+                             uint32_t *d_counts, uint64_t id_stride, uint64_t id_base, cudaStream_t s) {
+    const HostGraph &g = ix->g;
+    const uint64_t n = g.n;
+    if (nq == 0) return ZVDB_OK;
+    if (nq > 0x7FFFFFFFull) return fail(ZVDB_ERR_UNSUPPORTED, "nq exceeds 2^31-1 queries per launch");
+    if (k > 1024) return fail(ZVDB_ERR_UNSUPPORTED, "bruteforce: k > 1024");
+    const uint32_t pitch = g.row_floats;
+    // (1) operand split of the rows (once per index state) and of this query batch
+    if (ix->bf_rows != n) {
+        ZV_CUDA(ix->bf_xhi.reserve(n * pitch));
+        ZV_CUDA(ix->bf_xlo.reserve(n * pitch));
+        ZV_CUDA(ix->bf_xnorm.reserve(n));
+        const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((n + 7) / 8, 148ull * 16));
+        bf::split_tf32_kernel<<<blocks, 256, 0, s>>>(ix->d_arena, pitch, pitch, n, ix->bf_xhi.p, ix->bf_xlo.p, pitch, ix->bf_xnorm.p);
+        ix->launches++;
+        ZV_CUDA(cudaGetLastError());
+        ix->bf_rows = n;
+    }
+    ZV_CUDA(ix->bf_qhi.reserve(nq * pitch));
+    ZV_CUDA(ix->bf_qlo.reserve(nq * pitch));
+    {
+        const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((nq + 7) / 8, 148ull * 16));
+        bf::split_tf32_kernel<<<blocks, 256, 0, s>>>(d_q, g.dim, g.dim, nq, ix->bf_qhi.p, ix->bf_qlo.p, pitch, nullptr);
+        ix->launches++;
+        ZV_CUDA(cudaGetLastError());
+    }
+    // (2) work decomposition: (query tile, row split) items over one persistent CTA per SM
+    bf::BfParams p{};
+    p.n = static_cast<uint32_t>(n); p.nq = static_cast<uint32_t>(nq);
+    p.kchunks = pitch / bf::kBK;
+    p.kp = std::min<uint32_t>(k + bf::kSlack, static_cast<uint32_t>(std::max<uint64_t>(n, 1)));
+    p.n_qtiles = static_cast<uint32_t>((nq + bf::kBM - 1) / bf::kBM);
+    p.n_rtiles = static_cast<uint32_t>((n + bf::kBN - 1) / bf::kBN);
+    p.metric = g.metric;
+    const uint32_t max_splits = std::max<uint32_t>(1, std::min<uint32_t>(p.n_rtiles, std::min<uint32_t>(8192 / next_pow2(p.kp), 64)));
+    uint32_t best_s = 1; double best_eff = -1.0;
+    for (uint32_t sct = 1; sct <= max_splits; ++sct) {
+        const uint32_t tps = (p.n_rtiles + sct - 1) / sct;
+        const uint32_t real = (p.n_rtiles + tps - 1) / tps;          // splits that actually hold tiles
+        const uint64_t items = static_cast<uint64_t>(real) * p.n_qtiles;
+        const uint64_t waves = (items + ix->num_sms - 1) / ix->num_sms;
+        const double eff = static_cast<double>(items) / static_cast<double>(waves * ix->num_sms);
+        if (eff > best_eff + 0.03) { best_eff = eff; best_s = real; }
+    }
+    p.n_splits = best_s;
+    p.tiles_per_split = (p.n_rtiles + p.n_splits - 1) / p.n_splits;
+    p.n_splits = (p.n_rtiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    const uint64_t items = static_cast<uint64_t>(p.n_splits) * p.n_qtiles;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(items, ix->num_sms));
+    // (3) shared memory: ring stages + barriers + norms (+ the per-thread lists when they fit)
+    const size_t fixed = 1024 + 16 * sizeof(uint64_t) + 2 * bf::kBN * sizeof(float) + 64;
+    const size_t lists = static_cast<size_t>(p.kp) * 128 * sizeof(uint64_t);
+    bool lists_in_smem = fixed + lists + 2 * bf::kStageBytes <= ix->smem_optin;
+    size_t avail = ix->smem_optin - fixed - (lists_in_smem ? lists : 0);
+    p.stages = static_cast<uint32_t>(std::min<size_t>(bf::kMaxStages, avail / bf::kStageBytes));
+    if (p.stages < 2) return fail(ZVDB_ERR_UNSUPPORTED, "bruteforce: not enough shared memory for a 2-stage ring");
+    const size_t smem = fixed + p.stages * bf::kStageBytes + (lists_in_smem ? lists : 0);
+    if (!lists_in_smem) {
+        ZV_CUDA(ix->bf_glists.reserve(static_cast<size_t>(grid) * p.kp * 128));
+        p.glists = ix->bf_glists.p;
+    }
+    ZV_CUDA(ix->bf_part.reserve(static_cast<size_t>(p.n_splits) * nq * p.kp));
+    p.part_keys = ix->bf_part.p;
+    p.xnorm = ix->bf_xnorm.p;
+    CUtensorMap tm_qhi, tm_qlo, tm_xhi, tm_xlo;
+    int rc;
+    if ((rc = make_tile_map(&tm_qhi, ix->bf_qhi.p, nq, pitch))) return rc;
+    if ((rc = make_tile_map(&tm_qlo, ix->bf_qlo.p, nq, pitch))) return rc;
+    if ((rc = make_tile_map(&tm_xhi, ix->bf_xhi.p, n, pitch))) return rc;
+    if ((rc = make_tile_map(&tm_xlo, ix->bf_xlo.p, n, pitch))) return rc;
+    ZV_CUDA(cudaFuncSetAttribute(bf::bf_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    bf::bf_gemm_topk_kernel<<<grid, bf::kThreads, smem, s>>>(tm_qhi, tm_qlo, tm_xhi, tm_xlo, p);
+    ix->launches++;
+    ZV_CUDA(cudaGetLastError());
+    // (4) merge the splits, exact re-rank, write k
+    bf::BfFinalParams fp{};
+    fp.arena = reinterpret_cast<const float4 *>(ix->d_arena);
+    fp.queries = d_q; fp.part_keys = p.part_keys;
+    fp.ids = d_ids; fp.dist = d_dist; fp.counts = d_counts;
+    fp.id_stride = id_stride; fp.id_base = id_base;
+    fp.row_chunks = pitch / 4; fp.dim = g.dim; fp.nq = p.nq; fp.k = k; fp.kp = p.kp; fp.n_splits = p.n_splits;
+    fp.p2 = next_pow2(p.n_splits * p.kp); fp.kk2 = std::max<uint32_t>(2, next_pow2(k + bf::kSlack));
+    const uint32_t cpl_raw = (fp.row_chunks + 31) / 32;
+    const int cpl = cpl_raw <= 1 ? 1 : cpl_raw <= 2 ? 2 : cpl_raw <= 4 ? 4 : cpl_raw <= 6 ? 6 : 8;
+    const size_t fsmem = (static_cast<size_t>(fp.p2) + fp.kk2) * sizeof(uint64_t);
+    cudaError_t e = g.metric == 0 ? launch_bf_final_metric<kMetricL2>(cpl, fp, fsmem, s)
+                  : g.metric == 1 ? launch_bf_final_metric<kMetricCos>(cpl, fp, fsmem, s)
+                                  : launch_bf_final_metric<kMetricDot>(cpl, fp, fsmem, s);
+    ix->launches++;
+    ZV_CUDA(e);
+    return ZVDB_OK;
+}
+
 }  // namespace zvdb
 
 // ================================ exported C ABI ================================================
@@ -370,6 +523,7 @@ void zvdb_destroy(zvdb_index *ix) {
     cudaFree(ix->d_arena); cudaFree(ix->d_adj);
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
     ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_();
+    ix->bf_xhi.free_(); ix->bf_xlo.free_(); ix->bf_xnorm.free_(); ix->bf_qhi.free_(); ix->bf_qlo.free_(); ix->bf_part.free_(); ix->bf_glists.free_();
     delete ix;
 }
 
@@ -493,7 +647,7 @@ static int set_points_locked(zvdb_index *ix, const float *points, uint64_t n, ui
     }
     g.has_entry = n > 0; g.entry = entry; g.max_level = 0;
     g.rows_uploaded = 0; g.adj_all_dirty = true;
-    ix->n_dev = 0;
+    ix->n_dev = 0; ix->bf_rows = 0;
     return ZVDB_OK;
 }
 
@@ -669,6 +823,57 @@ int zvdb_search(zvdb_index *ix, const float *query, uint32_t dim, uint32_t k, ui
         return ix ? ZVDB_OK : fail(ZVDB_ERR_INVALID, "null index");
     }
     return zvdb_search_batch(ix, query, 1, dim, k, k, ids, dist, count, nullptr, nullptr);
+}
+
+int zvdb_bruteforce_knn_device(zvdb_index *ix, const float *d_queries, uint64_t nq, uint32_t k, uint64_t *d_ids,
+                               float *d_dist, uint32_t *d_counts, uint64_t id_stride, uint64_t id_base, void *stream) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    if (nq == 0) return ZVDB_OK;
+    if (!d_queries || !d_ids || !d_dist || !d_counts) return fail(ZVDB_ERR_INVALID, "bruteforce: null buffer");
+    if (k == 0) return fail(ZVDB_ERR_INVALID, "bruteforce: k must be >= 1");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ZV_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ix->g.n == 0) {
+        ZV_CUDA(cudaMemsetAsync(d_counts, 0, nq * sizeof(uint32_t), s));
+        ZV_CUDA(cudaMemsetAsync(d_ids, 0xFF, nq * k * sizeof(uint64_t), s));
+        ZV_CUDA(cudaMemsetAsync(d_dist, 0, nq * k * sizeof(float), s));
+        return ZVDB_OK;
+    }
+    int rc = sync_device_locked(ix);
+    if (rc) return rc;
+    return launch_bruteforce(ix, d_queries, nq, k, d_ids, d_dist, d_counts, id_stride, id_base, s);
+}
+
+int zvdb_bruteforce_knn(zvdb_index *ix, const float *queries, uint64_t nq, uint32_t dim, uint32_t k, uint64_t *ids,
+                        float *dist, uint32_t *counts) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    if (nq == 0) return ZVDB_OK;
+    if (!queries || !ids || !dist || !counts) return fail(ZVDB_ERR_INVALID, "bruteforce: null buffer");
+    if (k == 0) return fail(ZVDB_ERR_INVALID, "bruteforce: k must be >= 1");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ZV_CUDA(cudaSetDevice(ix->device));
+    if (ix->g.n == 0) {
+        for (uint64_t i = 0; i < nq; ++i) counts[i] = 0;
+        for (uint64_t i = 0; i < nq * k; ++i) { ids[i] = ZVDB_INVALID_ID; dist[i] = 0.0f; }
+        return ZVDB_OK;
+    }
+    if (dim != ix->g.dim) return fail(ZVDB_ERR_DIM_MISMATCH, "Mismatched dimensions in distance calculation");
+    int rc = sync_device_locked(ix);
+    if (rc) return rc;
+    ZV_CUDA(ix->q_buf.reserve(nq * dim));
+    ZV_CUDA(ix->ids_buf.reserve(nq * k));
+    ZV_CUDA(ix->dist_buf.reserve(nq * k));
+    ZV_CUDA(ix->cnt_buf.reserve(nq));
+    cudaStream_t s = ix->stream;
+    ZV_CUDA(cudaMemcpyAsync(ix->q_buf.p, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = launch_bruteforce(ix, ix->q_buf.p, nq, k, ix->ids_buf.p, ix->dist_buf.p, ix->cnt_buf.p, 1, 0, s);
+    if (rc) return rc;
+    ZV_CUDA(cudaMemcpyAsync(ids, ix->ids_buf.p, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    ZV_CUDA(cudaMemcpyAsync(dist, ix->dist_buf.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    ZV_CUDA(cudaMemcpyAsync(counts, ix->cnt_buf.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ZV_CUDA(cudaStreamSynchronize(s));
+    return ZVDB_OK;
 }
 
 int zvdb_merge_topk_device(const float *d_dist, const uint64_t *d_ids, const uint32_t *d_counts, uint32_t G,

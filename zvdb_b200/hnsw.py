@@ -226,6 +226,26 @@ class HNSW:
         L.check(L.lib().zvdb_search_batch_device(self._h, d_queries, nq, k, ef, d_ids, d_dist, d_counts,
                                                  d_pops or None, d_evals or None, id_stride, id_base, stream or None))
 
+    # -- exact brute-force k-NN (K4; no reference counterpart) -----------------------------------------
+    def bruteforce_knn(self, queries, k: int):
+        """Exact k nearest rows per query on the tensor cores: (ids[nq,k] u64, dist[nq,k] f32, counts[nq])."""
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        nq, dim = q.shape
+        ids = np.empty((nq, k), np.uint64)
+        dist = np.empty((nq, k), np.float32)
+        counts = np.empty(nq, np.uint32)
+        L.check(L.lib().zvdb_bruteforce_knn(self._h, q.ctypes.data, nq, dim, k, ids.ctypes.data, dist.ctypes.data,
+                                            counts.ctypes.data))
+        return ids, dist, counts
+
+    def bruteforce_knn_device(self, d_queries: int, nq: int, k: int, d_ids: int, d_dist: int, d_counts: int,
+                              id_stride: int = 1, id_base: int = 0, stream: int = 0) -> None:
+        """zvdb_bruteforce_knn_device on raw DEVICE addresses; enqueued on `stream`, not synchronised."""
+        L.check(L.lib().zvdb_bruteforce_knn_device(self._h, d_queries, nq, k, d_ids, d_dist, d_counts, id_stride,
+                                                   id_base, stream or None))
+
     def sync_device(self) -> None:
         L.check(L.lib().zvdb_sync_device(self._h))
 

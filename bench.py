@@ -55,6 +55,8 @@ def parse_args():
     p.add_argument("--sweep", action="store_true", help="also report the ef sweep 32..512 (untimed extra passes)")
     p.add_argument("--variant", type=int, default=0, help="search kernel variant: 0 auto, 1 narrow, 2 wide")
     p.add_argument("--cpu-sample", type=int, default=2000, help="queries in the CPU-baseline sample")
+    p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                   help="N>1: fused peer-store exchange inside the search kernel, or one NCCL all-gather")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return p.parse_args()
 
@@ -76,12 +78,13 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_traffic(ef):
-    """dram bytes per launch from the committed ncu --set full capture, if one matches this ef."""
+def load_traffic(graph, n, dim, m, nq, ef):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the search kernel, from the committed
+    ncu --set full capture of this exact configuration (profiles/traffic.json), else None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         t = json.load(open(path))
-        return t.get(str(ef))
+        return t.get(f"{graph}:n={n}:dim={dim}:m={m}:nq={nq}:ef={ef}")
     except Exception:
         return None
 
@@ -142,19 +145,6 @@ def recall_at_k(ids, gt):
     for a, b in zip(ids, gt):
         hit += len(set(a[:k].tolist()) & set(b.tolist()))
     return hit / (len(gt) * k)
-
-
-def exact_knn_torch(X_dev, Q, k, chunk=2000):
-    """Ground truth for recall only (outside every timed region): fp32 matmul + topk on the GPU."""
-    import torch
-    torch.backends.cuda.matmul.allow_tf32 = False
-    xn = (X_dev * X_dev).sum(1)
-    out = []
-    for s in range(0, len(Q), chunk):
-        q = torch.from_numpy(Q[s:s + chunk]).to(X_dev.device)
-        d = xn[None, :] - 2.0 * (q @ X_dev.T)
-        out.append(torch.topk(d, k, dim=1, largest=False).indices.cpu().numpy())
-    return np.concatenate(out).astype(np.uint64)
 
 
 def algorithmic_bytes(evals, pops, row_bytes, m, dim, k):
@@ -245,28 +235,44 @@ def run_ours(args):
     d_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
     d_pops = torch.empty(nq, dtype=torch.int32, device=dev)
     d_evals = torch.empty(nq, dtype=torch.int32, device=dev)
+    backend = None
     if world > 1:
-        g_ids = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-        g_dist = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
-        g_cnt = torch.empty((world, nq), dtype=torch.int32, device=dev)
+        from zvdb_b200.sharded import CudaBackend, block_bytes
+        backend = CudaBackend(h, rank, world)
         m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         m_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
         m_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+        if args.exchange == "p2p":
+            backend.open_exchange(nq, k, None)
+        else:
+            blk = torch.empty(block_bytes(nq, k), dtype=torch.uint8, device=dev)
+            gathered = torch.empty(world * block_bytes(nq, k), dtype=torch.uint8, device=dev)
 
     launches = [0]
 
-    def step(b, e=None):
+    def search_only(b, e=None):
         e = ef_shard if e is None else e
         h.search_batch_device(dq[b].data_ptr(), nq, k, e, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(),
                               d_pops.data_ptr(), d_evals.data_ptr(), id_stride=world, id_base=rank, stream=stream)
-        launches[0] += 1
-        if world > 1:
-            dist.all_gather_into_tensor(g_ids, d_ids)
-            dist.all_gather_into_tensor(g_dist, d_dist)
-            dist.all_gather_into_tensor(g_cnt, d_cnt)
-            zvdb_b200.merge_topk_device(g_dist.data_ptr(), g_ids.data_ptr(), g_cnt.data_ptr(), world, nq, k,
-                                        m_dist.data_ptr(), m_ids.data_ptr(), m_cnt.data_ptr(), stream)
+
+    def step(b, e=None, q=None):
+        """One pass of the hot path over query batch b (device-resident unless q is given)."""
+        e = ef_shard if e is None else e
+        q = dq[b] if q is None else q
+        if world == 1:
+            h.search_batch_device(q.data_ptr(), nq, k, e, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(),
+                                  d_pops.data_ptr(), d_evals.data_ptr(), stream=stream)
             launches[0] += 1
+        elif args.exchange == "p2p":
+            backend.search_exchange(q, nq, k, e, out=(m_ids, m_dist, m_cnt))      # search(+peer stores), signal, merge
+            launches[0] += 3
+        else:
+            zvdb_b200._lib.check(zvdb_b200.lib().zvdb_search_batch_packed_device(h._h, q.data_ptr(), nq, k, e, blk.data_ptr(),
+                                                                                 world, rank, stream))
+            dist.all_gather_into_tensor(gathered, blk)
+            zvdb_b200._lib.check(zvdb_b200.lib().zvdb_merge_topk_packed_device(gathered.data_ptr(), world, nq, k, m_dist.data_ptr(),
+                                                                               m_ids.data_ptr(), m_cnt.data_ptr(), stream))
+            launches[0] += 2
 
     def barrier():
         if world > 1:
@@ -274,17 +280,40 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- untimed: counters (roofline numerator) and recall for each query batch -----------------
-    X_dev = torch.from_numpy(X).to(dev) if rank == 0 else None
+    def exact_ground_truth(b):
+        """Exact top-k of query batch b over the WHOLE index by our own brute-force kernel (K4, tcgen05):
+        per shard, then the same exchange + merge as the search results. Untimed."""
+        from zvdb_b200.sharded import block_bytes
+        bb = block_bytes(nq, k)
+        g_blk = torch.empty(bb, dtype=torch.uint8, device=dev)
+        p0 = g_blk.data_ptr()
+        h.bruteforce_knn_device(dq[b].data_ptr(), nq, k, p0, p0 + nq * k * 8, p0 + nq * k * 12,
+                                id_stride=world, id_base=rank, stream=stream)
+        if world > 1:
+            g_all = torch.empty(world * bb, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(g_all, g_blk)
+        else:
+            g_all = g_blk
+        o_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        o_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        o_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+        zvdb_b200._lib.check(zvdb_b200.lib().zvdb_merge_topk_packed_device(g_all.data_ptr(), world, nq, k, o_dist.data_ptr(),
+                                                                           o_ids.data_ptr(), o_cnt.data_ptr(), stream))
+        torch.cuda.synchronize()
+        return o_ids.cpu().numpy().view(np.uint64)
+
     bytes_per_batch, evals_mean, pops_mean, recalls = [], [], [], []
     for b in range(QUERY_BATCHES):
         step(b)
+        if world > 1:
+            search_only(b)                      # same shard-local search again, with the counters
         torch.cuda.synchronize()
         ev, po = d_evals.cpu().numpy().view(np.uint32), d_pops.cpu().numpy().view(np.uint32)
         bytes_per_batch.append(algorithmic_bytes(ev, po, row_bytes, args.m, args.dim, k))
         evals_mean.append(float(ev.mean())); pops_mean.append(float(po.mean()))
-        if rank == 0 and b == 0:
-            gt = exact_knn_torch(X_dev, Qs[0], k)
-            res = (m_ids if world > 1 else d_ids).cpu().numpy().view(np.uint64)
+        if b == 0:
+            res = (m_ids if world > 1 else d_ids).cpu().numpy().view(np.uint64).copy()
+            gt = exact_ground_truth(0)
             recalls.append(recall_at_k(res, gt))
     sweep = None
     if args.sweep and rank == 0 and world == 1:
@@ -300,7 +329,6 @@ def run_ours(args):
             by = algorithmic_bytes(ev, po, row_bytes, args.m, args.dim, k)
             sweep.append({"ef": e, "qps": nq / (ms * 1e-3), "recall_at_10": recall_at_k(d_ids.cpu().numpy().view(np.uint64), gt),
                           "evals_per_query": float(ev.mean()), "hbm_gbs": by / (ms * 1e-3) / 1e9})
-    del X_dev
     torch.cuda.empty_cache()
 
     # ---- timed region: W warm-up steps, then exactly K steps --------------------------------------
@@ -331,28 +359,58 @@ def run_ours(args):
     dev_ms_max = float(t.item())
     gpu_launches = launches[0]
 
-    # ---- e2e: the host-buffer C-ABI call, pinned host memory, copies inside the timed region -----
-    e2e = None
-    if world == 1:
-        hq = [torch.from_numpy(q).pin_memory() for q in Qs]
-        h_ids = torch.empty((nq, k), dtype=torch.int64).pin_memory()
-        h_dist = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-        h_cnt = torch.empty(nq, dtype=torch.int32).pin_memory()
-        for w in range(args.warmup):
-            h.search_batch_ptr(hq[w % QUERY_BATCHES].data_ptr(), nq, args.dim, k, ef, h_ids.data_ptr(),
-                               h_dist.data_ptr(), h_cnt.data_ptr())
+    # ---- kernel-only time of the dominant kernel (the shard-local search) for the roofline ------------
+    if world > 1:
+        for w in range(3):
+            search_only(w % QUERY_BATCHES)
         torch.cuda.synchronize()
-        t_e = time.perf_counter()
-        for s in range(args.steps):
-            h.search_batch_ptr(hq[s % QUERY_BATCHES].data_ptr(), nq, args.dim, k, ef, h_ids.data_ptr(),
-                               h_dist.data_ptr(), h_cnt.data_ptr())
+        ks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ke = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for s_ in range(args.steps):
+            ks[s_].record(); search_only(s_ % QUERY_BATCHES); ke[s_].record()
         torch.cuda.synchronize()
-        e_dt = time.perf_counter() - t_e
-        e2e = {"value": nq * args.steps / e_dt, "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4,
-               "d2h_bytes_per_step": nq * k * 12 + nq * 4}
+        kern_ms = [ks[s_].elapsed_time(ke[s_]) for s_ in range(args.steps)]
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region ----------------------
+    hq = [torch.from_numpy(q).pin_memory() for q in Qs]
+    h_ids = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    h_dist = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty(nq, dtype=torch.int32).pin_memory()
+    if world > 1:
+        q_dev = torch.empty((nq, args.dim), dtype=torch.float32, device=dev)
+
+    def e2e_step(b):
+        if world == 1:      # the reference-facing call: zvdb_search_batch on HOST pointers
+            h.search_batch_ptr(hq[b].data_ptr(), nq, args.dim, k, ef, h_ids.data_ptr(), h_dist.data_ptr(), h_cnt.data_ptr())
+        else:               # every rank: H2D of the batch, sharded search + exchange + merge, D2H of the merged top-k
+            q_dev.copy_(hq[b], non_blocking=True)
+            step(b, q=q_dev)
+            h_ids.copy_(m_ids, non_blocking=True); h_dist.copy_(m_dist, non_blocking=True); h_cnt.copy_(m_cnt, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    for w in range(args.warmup):
+        e2e_step(w % QUERY_BATCHES)
+    barrier()
+    t_e = time.perf_counter()
+    for s_ in range(args.steps):
+        e2e_step(s_ % QUERY_BATCHES)
+    barrier()
+    e_dt = torch.tensor([time.perf_counter() - t_e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": nq * args.steps / float(e_dt.item()), "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4 * world,
+           "d2h_bytes_per_step": (nq * k * 12 + nq * 4) * world,
+           "api": "zvdb_search_batch (host pointers)" if world == 1 else
+                  f"per rank: pinned H2D + zvdb_search_batch_{'exchange' if args.exchange == 'p2p' else 'packed_device + all_gather + merge'} + D2H"}
+    if world > 1:
+        tb = torch.tensor([float(np.mean(bytes_per_batch))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tb)                      # algorithmic bytes of the whole job (all shards)
+        job_bytes = float(tb.item())
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
+            backend.close()
             dist.destroy_process_group()
         return
 
@@ -387,21 +445,24 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.n}x{args.dim} fp32 L2 synthetic Gaussian, M={args.m}, {nq}-query batch, k={k}, "
-                               f"ef={ef}" + (f" ({ef_shard}/shard, id-sharded over {world} GPUs, all-gather + merge)" if world > 1 else ""),
+                               f"ef={ef}" + (f" ({ef_shard} pops/shard, id-sharded over {world} GPUs, exchange={args.exchange})" if world > 1 else ""),
                    "graph": "reference insert (hnsw.zig:73-170)" if args.graph == "reference" else "quality builder",
                    "l2_policy": f"index {args.n * args.dim * 4 / 1e6:.0f} MB > 126 MB L2; {QUERY_BATCHES} query batches rotated",
                    "recall_at_10": recalls[0] if recalls else None,
                    "evals_per_query": float(np.mean(evals_mean)), "pops_per_query": float(np.mean(pops_mean)),
                    "build_seconds": build_s, "wall_ms_per_step": 1e3 * wall / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": load_traffic(ef), "peak_source": peak_src, "kernel": "search_layer0_kernel",
-                     "algorithmic_bytes_per_launch": mean_bytes, "avg_launch_ms": avg_kernel_s * 1e3},
+                     "traffic": load_traffic(args.graph, args.n, args.dim, args.m, nq, ef) if world == 1 else None, "peak_source": peak_src, "kernel": "search_layer0_kernel",
+                     "algorithmic_bytes_per_launch": mean_bytes, "avg_launch_ms": avg_kernel_s * 1e3,
+                     "scope": "rank 0's shard-local search kernel" if world > 1 else "the whole step"},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
     }
     if sweep:
         line["sweep"] = sweep
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
+        backend.close()
         dist.destroy_process_group()
 
 

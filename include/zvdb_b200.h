@@ -182,6 +182,38 @@ ZVDB_API int zvdb_merge_topk_device(const float *d_dist, const uint64_t *d_ids, 
                                     uint32_t G, uint64_t nq, uint32_t k, float *out_dist, uint64_t *out_ids,
                                     uint32_t *out_counts, void *stream);
 
+/* Packed per-shard result block for nq queries x k: ids u64[nq*k] | dist f32[nq*k] | counts u32[nq],
+ * padded to zvdb_shard_block_bytes(nq, k) (a multiple of 256). One all-gather of such blocks, or
+ * the exchange below, moves a shard's whole top-k. */
+ZVDB_API uint64_t zvdb_shard_block_bytes(uint64_t nq, uint32_t k);
+
+/* zvdb_search_batch_device writing its three outputs into one packed block (device memory). */
+ZVDB_API int zvdb_search_batch_packed_device(zvdb_index *ix, const float *d_queries, uint64_t nq, uint32_t k,
+                                             uint32_t ef, void *d_block, uint64_t id_stride, uint64_t id_base,
+                                             void *stream);
+
+/* zvdb_merge_topk_device over G packed blocks laid out back to back (the output of ONE all-gather). */
+ZVDB_API int zvdb_merge_topk_packed_device(const void *d_blocks, uint32_t G, uint64_t nq, uint32_t k, float *out_dist,
+                                           uint64_t *out_ids, uint32_t *out_counts, void *stream);
+
+/* ---- fused search + all-gather over NVLink peer memory --------------------------------
+ * One process per GPU. Each rank creates an exchange (a gather buffer in its own HBM), publishes
+ * its 64-byte CUDA IPC handle, and opens every peer's. zvdb_search_batch_exchange then runs the
+ * shard-local search with an epilogue that stores the shard's top-k directly into block `rank` of
+ * EVERY rank's gather buffer (peer-mapped st.global over NVLink/NVSwitch: the all-gather happens
+ * inside the search kernel, no collective call), publishes a per-rank flag (release, system scope),
+ * and launches the merge kernel, which waits on the G flags (acquire) before merging. All ranks
+ * obtain the merged top-k. Ranks must call it the same number of times with the same nq and k. */
+typedef struct zvdb_exchange zvdb_exchange;
+ZVDB_API int zvdb_exchange_create(zvdb_exchange **out, int device, uint32_t world, uint32_t rank, uint64_t nq_max,
+                                  uint32_t k_max);
+ZVDB_API int zvdb_exchange_ipc_handle(zvdb_exchange *ex, void *handle64);          /* writes 64 bytes */
+ZVDB_API int zvdb_exchange_open_peers(zvdb_exchange *ex, const void *handles);     /* world x 64 bytes, rank order */
+ZVDB_API void zvdb_exchange_destroy(zvdb_exchange *ex);
+ZVDB_API int zvdb_search_batch_exchange(zvdb_index *ix, zvdb_exchange *ex, const float *d_queries, uint64_t nq,
+                                        uint32_t k, uint32_t ef, uint64_t *out_ids, float *out_dist,
+                                        uint32_t *out_counts, void *stream);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 
 /* Message of the last failure on the calling thread ("" if none). Never NULL. */

@@ -44,6 +44,14 @@ SIGNATURES = {
     "zvdb_set_kernel_variant": (_i32, [_vp, _u32]),
     "zvdb_kernel_launches": (_u64, [_vp]),
     "zvdb_merge_topk_device": (_i32, [_vp, _vp, _vp, _u32, _u64, _u32, _vp, _vp, _vp, _vp]),
+    "zvdb_shard_block_bytes": (_u64, [_u64, _u32]),
+    "zvdb_search_batch_packed_device": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _u64, _u64, _vp]),
+    "zvdb_merge_topk_packed_device": (_i32, [_vp, _u32, _u64, _u32, _vp, _vp, _vp, _vp]),
+    "zvdb_exchange_create": (_i32, [C.POINTER(_vp), _i32, _u32, _u32, _u64, _u32]),
+    "zvdb_exchange_ipc_handle": (_i32, [_vp, _vp]),
+    "zvdb_exchange_open_peers": (_i32, [_vp, _vp]),
+    "zvdb_exchange_destroy": (None, [_vp]),
+    "zvdb_search_batch_exchange": (_i32, [_vp, _vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp]),
     "zvdb_last_error": (C.c_char_p, []),
     "zvdb_version": (C.c_char_p, []),
 }

@@ -190,7 +190,7 @@ static cudaError_t launch_search_wv(int metric, int cpl, const SearchParams &p, 
 // the device copy.
 static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t *d_ids,
                          float *d_dist, uint32_t *d_counts, uint32_t *d_pops, uint32_t *d_evals, uint64_t id_stride,
-                         uint64_t id_base, cudaStream_t s) {
+                         uint64_t id_base, cudaStream_t s, uint8_t *const *peer_blocks = nullptr, uint32_t n_peers = 0) {
     const HostGraph &g = ix->g;
     if (nq == 0) return ZVDB_OK;
     if (nq > 0x7FFFFFFFull) return fail(ZVDB_ERR_UNSUPPORTED, "nq exceeds 2^31-1 queries per launch");
@@ -200,6 +200,8 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     p.queries = d_q;
     p.ids = d_ids; p.dist = d_dist; p.counts = d_counts; p.pops = d_pops; p.evals = d_evals;
     p.id_stride = id_stride; p.id_base = id_base;
+    p.n_peers = n_peers;
+    for (uint32_t i = 0; i < n_peers && i < 8; ++i) p.peer_blocks[i] = peer_blocks[i];
     p.row_chunks = g.row_floats / 4;
     p.m = g.m; p.n = static_cast<uint32_t>(g.n); p.entry = static_cast<uint32_t>(g.entry); p.dim = g.dim;
     p.nq = static_cast<uint32_t>(nq); p.k = k; p.ef = ef;
@@ -270,29 +272,43 @@ struct MergeLess {
 };
 
 // One CTA per query: gather the G shard lists into shared memory, bitonic-sort them by
-// (distance, global id), write the first k.
-__global__ void merge_topk_kernel(const float *__restrict__ d_dist, const uint64_t *__restrict__ d_ids,
-                                  const uint32_t *__restrict__ d_counts, uint32_t G, uint32_t nq, uint32_t k,
-                                  float *__restrict__ out_dist, uint64_t *__restrict__ out_ids,
-                                  uint32_t *__restrict__ out_counts, uint32_t p2) {
+// (distance, global id), write the first k. The G lists are addressed as base + g * stride (bytes),
+// which covers both the three separate [G][nq][k] arrays of zvdb_merge_topk_device and the packed
+// per-rank blocks of the exchange buffer. With `flags` set, the CTA first waits until every rank
+// has published `epoch` (system-scope acquire), i.e. until all peers' stores have landed.
+__global__ void merge_topk_kernel(const uint8_t *__restrict__ dist_base, const uint8_t *__restrict__ ids_base,
+                                  const uint8_t *__restrict__ cnt_base, uint64_t dist_stride, uint64_t ids_stride,
+                                  uint64_t cnt_stride, uint32_t G, uint32_t nq, uint32_t k, float *__restrict__ out_dist,
+                                  uint64_t *__restrict__ out_ids, uint32_t *__restrict__ out_counts, uint32_t p2,
+                                  const uint32_t *flags, uint32_t flag_pitch, uint32_t epoch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);   // [p2]  ordered(dist) << 32 | slot
     uint64_t *gid = keys + p2;                                 // [G*k]
     const uint32_t q = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    if (flags) {
+        if (tid < G) {
+            uint32_t v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + static_cast<size_t>(tid) * flag_pitch) : "memory");
+            } while (static_cast<int32_t>(v - epoch) < 0);
+        }
+        __syncthreads();
+    }
     const uint32_t total = G * k;
     for (uint32_t i = tid; i < p2; i += T) {
         uint64_t key = ~0ull;
         if (i < total) {
             const uint32_t gsh = i / k, j = i % k;
-            const size_t src = (static_cast<size_t>(gsh) * nq + q) * k + j;
-            gid[i] = d_ids[src];
-            if (j < d_counts[static_cast<size_t>(gsh) * nq + q]) key = (static_cast<uint64_t>(float_to_ordered(d_dist[src])) << 32) | i;
+            const size_t src = static_cast<size_t>(q) * k + j;
+            gid[i] = reinterpret_cast<const uint64_t *>(ids_base + gsh * ids_stride)[src];
+            if (j < reinterpret_cast<const uint32_t *>(cnt_base + gsh * cnt_stride)[q])
+                key = (static_cast<uint64_t>(float_to_ordered(reinterpret_cast<const float *>(dist_base + gsh * dist_stride)[src])) << 32) | i;
         }
         keys[i] = key;
     }
     bitonic_sort_u64(keys, p2, MergeLess{gid});
     uint32_t valid = 0;
-    for (uint32_t gsh = 0; gsh < G; ++gsh) valid += min(d_counts[static_cast<size_t>(gsh) * nq + q], k);
+    for (uint32_t gsh = 0; gsh < G; ++gsh) valid += min(reinterpret_cast<const uint32_t *>(cnt_base + gsh * cnt_stride)[q], k);
     const uint32_t nres = min(valid, k);
     for (uint32_t r = tid; r < k; r += T) {
         const size_t o = static_cast<size_t>(q) * k + r;
@@ -306,6 +322,34 @@ __global__ void merge_topk_kernel(const float *__restrict__ d_dist, const uint64
         }
     }
     if (tid == 0) out_counts[q] = nres;
+}
+
+// After this rank's search kernel (stream order), publish `epoch` in slot `rank` of every peer's
+// flag array: system-scope release, so the search kernel's peer stores are visible first.
+__global__ void exchange_signal_kernel(uint32_t *const *peer_flags, uint32_t world, uint32_t rank, uint32_t flag_pitch, uint32_t epoch) {
+    if (threadIdx.x < world) {
+        __threadfence_system();
+        uint32_t *f = peer_flags[threadIdx.x] + static_cast<size_t>(rank) * flag_pitch;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+}
+
+static int launch_merge(const uint8_t *dist_base, const uint8_t *ids_base, const uint8_t *cnt_base, uint64_t dist_stride,
+                        uint64_t ids_stride, uint64_t cnt_stride, uint32_t G, uint64_t nq, uint32_t k, float *out_dist,
+                        uint64_t *out_ids, uint32_t *out_counts, cudaStream_t s, const uint32_t *flags, uint32_t flag_pitch,
+                        uint32_t epoch) {
+    const uint64_t total = static_cast<uint64_t>(G) * k;
+    if (total > 4096) return fail(ZVDB_ERR_UNSUPPORTED, "merge: G*k > 4096");
+    const uint32_t p2 = next_pow2(static_cast<uint32_t>(total));
+    const size_t smem = static_cast<size_t>(p2) * 8 + total * 8;
+    const unsigned threads = p2 >= 512 ? 256 : (p2 >= 128 ? 64 : 32);
+    if (smem > 48 * 1024)
+        ZV_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    merge_topk_kernel<<<static_cast<unsigned>(nq), threads, smem, s>>>(dist_base, ids_base, cnt_base, dist_stride, ids_stride,
+                                                                      cnt_stride, G, static_cast<uint32_t>(nq), k, out_dist,
+                                                                      out_ids, out_counts, p2, flags, flag_pitch, epoch);
+    ZV_CUDA(cudaGetLastError());
+    return ZVDB_OK;
 }
 
 template <int CPL, int METRIC>
@@ -882,17 +926,145 @@ int zvdb_merge_topk_device(const float *d_dist, const uint64_t *d_ids, const uin
     if (!d_dist || !d_ids || !d_counts || !out_dist || !out_ids || !out_counts) return fail(ZVDB_ERR_INVALID, "merge: null buffer");
     if (G == 0 || k == 0) return fail(ZVDB_ERR_INVALID, "merge: G and k must be >= 1");
     if (nq == 0) return ZVDB_OK;
-    const uint64_t total = static_cast<uint64_t>(G) * k;
-    if (total > 4096) return fail(ZVDB_ERR_UNSUPPORTED, "merge: G*k > 4096");
-    const uint32_t p2 = next_pow2(static_cast<uint32_t>(total));
-    const size_t smem = static_cast<size_t>(p2) * 8 + total * 8;
-    const unsigned threads = p2 >= 512 ? 256 : (p2 >= 128 ? 64 : 32);
-    if (smem > 48 * 1024)
-        ZV_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    merge_topk_kernel<<<static_cast<unsigned>(nq), threads, smem, static_cast<cudaStream_t>(stream)>>>(
-        d_dist, d_ids, d_counts, G, static_cast<uint32_t>(nq), k, out_dist, out_ids, out_counts, p2);
-    ZV_CUDA(cudaGetLastError());
+    return launch_merge(reinterpret_cast<const uint8_t *>(d_dist), reinterpret_cast<const uint8_t *>(d_ids),
+                        reinterpret_cast<const uint8_t *>(d_counts), nq * k * sizeof(float), nq * k * sizeof(uint64_t),
+                        nq * sizeof(uint32_t), G, nq, k, out_dist, out_ids, out_counts, static_cast<cudaStream_t>(stream),
+                        nullptr, 0, 0);
+}
+
+uint64_t zvdb_shard_block_bytes(uint64_t nq, uint32_t k) {
+    return (nq * k * 12 + nq * 4 + 255) / 256 * 256;
+}
+
+int zvdb_merge_topk_packed_device(const void *d_blocks, uint32_t G, uint64_t nq, uint32_t k, float *out_dist,
+                                  uint64_t *out_ids, uint32_t *out_counts, void *stream) {
+    if (!d_blocks || !out_dist || !out_ids || !out_counts) return fail(ZVDB_ERR_INVALID, "merge: null buffer");
+    if (G == 0 || k == 0) return fail(ZVDB_ERR_INVALID, "merge: G and k must be >= 1");
+    if (nq == 0) return ZVDB_OK;
+    const uint8_t *b = static_cast<const uint8_t *>(d_blocks);
+    const uint64_t stride = zvdb_shard_block_bytes(nq, k);
+    return launch_merge(b + nq * k * 8, b, b + nq * k * 12, stride, stride, stride, G, nq, k, out_dist, out_ids, out_counts,
+                        static_cast<cudaStream_t>(stream), nullptr, 0, 0);
+}
+
+int zvdb_search_batch_packed_device(zvdb_index *ix, const float *d_queries, uint64_t nq, uint32_t k, uint32_t ef,
+                                    void *d_block, uint64_t id_stride, uint64_t id_base, void *stream) {
+    if (!d_block) return fail(ZVDB_ERR_INVALID, "search: null block");
+    uint8_t *b = static_cast<uint8_t *>(d_block);
+    return zvdb_search_batch_device(ix, d_queries, nq, k, ef, reinterpret_cast<uint64_t *>(b),
+                                    reinterpret_cast<float *>(b + nq * k * 8), reinterpret_cast<uint32_t *>(b + nq * k * 12),
+                                    nullptr, nullptr, id_stride, id_base, stream);
+}
+
+// ---- exchange: gather buffers mapped into every peer (CUDA IPC), for the fused all-gather ----------
+
+struct zvdb_exchange {
+    int device = 0;
+    uint32_t world = 1, rank = 0;
+    uint64_t cap_bytes = 0;          // bytes of one parity half: world blocks
+    uint8_t *local = nullptr;        // [2][world][block] | flags
+    uint64_t flags_off = 0;
+    uint8_t *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t **d_peer_flags = nullptr;   // device array of world pointers
+    uint32_t epoch = 0;
+    bool opened = false;
+};
+static constexpr uint32_t kFlagPitch = 32;   // one flag per 128 bytes
+
+int zvdb_exchange_create(zvdb_exchange **out, int device, uint32_t world, uint32_t rank, uint64_t nq_max, uint32_t k_max) {
+    if (!out) return fail(ZVDB_ERR_INVALID, "exchange: out is null");
+    *out = nullptr;
+    if (world == 0 || world > 8 || rank >= world) return fail(ZVDB_ERR_INVALID, "exchange: world must be 1..8 and rank < world");
+    ZV_CUDA(cudaSetDevice(device));
+    zvdb_exchange *ex = new (std::nothrow) zvdb_exchange();
+    if (!ex) return fail(ZVDB_ERR_OUT_OF_MEMORY, "exchange: out of memory");
+    ex->device = device; ex->world = world; ex->rank = rank;
+    ex->cap_bytes = zvdb_shard_block_bytes(nq_max, k_max) * world;
+    ex->flags_off = 2 * ex->cap_bytes;
+    const size_t total = ex->flags_off + static_cast<size_t>(world) * kFlagPitch * sizeof(uint32_t);
+    cudaError_t e = cudaMalloc(&ex->local, total);
+    if (e == cudaSuccess) e = cudaMemset(ex->local, 0, total);
+    if (e == cudaSuccess) e = cudaMalloc(&ex->d_peer_flags, 8 * sizeof(uint32_t *));
+    if (e != cudaSuccess) { cudaFree(ex->local); delete ex; ZV_CUDA(e); }
+    ex->peer[rank] = ex->local;
+    *out = ex;
     return ZVDB_OK;
+}
+
+int zvdb_exchange_ipc_handle(zvdb_exchange *ex, void *handle64) {
+    if (!ex || !handle64) return fail(ZVDB_ERR_INVALID, "exchange: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    ZV_CUDA(cudaSetDevice(ex->device));
+    cudaIpcMemHandle_t h;
+    ZV_CUDA(cudaIpcGetMemHandle(&h, ex->local));
+    std::memcpy(handle64, &h, 64);
+    return ZVDB_OK;
+}
+
+int zvdb_exchange_open_peers(zvdb_exchange *ex, const void *handles) {
+    if (!ex || !handles) return fail(ZVDB_ERR_INVALID, "exchange: null argument");
+    ZV_CUDA(cudaSetDevice(ex->device));
+    for (uint32_t g = 0; g < ex->world; ++g) {
+        if (g == ex->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const uint8_t *>(handles) + 64 * g, 64);
+        void *p = nullptr;
+        ZV_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ex->peer[g] = static_cast<uint8_t *>(p);
+    }
+    uint32_t *pf[8] = {};
+    for (uint32_t g = 0; g < ex->world; ++g) pf[g] = reinterpret_cast<uint32_t *>(ex->peer[g] + ex->flags_off);
+    ZV_CUDA(cudaMemcpy(ex->d_peer_flags, pf, sizeof(pf), cudaMemcpyHostToDevice));
+    ex->opened = true;
+    return ZVDB_OK;
+}
+
+void zvdb_exchange_destroy(zvdb_exchange *ex) {
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    cudaDeviceSynchronize();
+    for (uint32_t g = 0; g < ex->world; ++g)
+        if (g != ex->rank && ex->peer[g]) cudaIpcCloseMemHandle(ex->peer[g]);
+    cudaFree(ex->d_peer_flags);
+    cudaFree(ex->local);
+    delete ex;
+}
+
+int zvdb_search_batch_exchange(zvdb_index *ix, zvdb_exchange *ex, const float *d_queries, uint64_t nq, uint32_t k,
+                               uint32_t ef, uint64_t *out_ids, float *out_dist, uint32_t *out_counts, void *stream) {
+    if (!ix || !ex) return fail(ZVDB_ERR_INVALID, "null argument");
+    if (!ex->opened && ex->world > 1) return fail(ZVDB_ERR_INVALID, "exchange: peers not opened");
+    if (nq == 0) return ZVDB_OK;
+    if (!d_queries || !out_ids || !out_dist || !out_counts) return fail(ZVDB_ERR_INVALID, "search: null buffer");
+    if (k == 0) return fail(ZVDB_ERR_INVALID, "search: k must be >= 1");
+    if (ef == 0) ef = k;
+    if (ef < k) return fail(ZVDB_ERR_INVALID, "search: ef must be >= k");
+    const uint64_t block = zvdb_shard_block_bytes(nq, k);
+    if (block * ex->world > ex->cap_bytes) return fail(ZVDB_ERR_INVALID, "exchange: nq * k exceeds the capacity the exchange was created with");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ZV_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t epoch = ++ex->epoch;
+    const uint64_t half = (epoch & 1) * ex->cap_bytes;           // double buffered: a peer may already be one call ahead
+    uint8_t *blocks[8];
+    for (uint32_t g = 0; g < ex->world; ++g) blocks[g] = ex->peer[g] + half + block * ex->rank;
+    if (ix->g.n == 0 || !ix->g.has_entry) {
+        // an empty shard still publishes count 0 for every query (memset through the peer mappings)
+        for (uint32_t g = 0; g < ex->world; ++g) ZV_CUDA(cudaMemsetAsync(blocks[g] + nq * k * 12, 0, nq * sizeof(uint32_t), s));
+    } else {
+        int rc = sync_device_locked(ix);
+        if (rc) return rc;
+        rc = launch_search(ix, d_queries, nq, k, ef, nullptr, nullptr, nullptr, nullptr, nullptr, ex->world, ex->rank, s, blocks, ex->world);
+        if (rc) return rc;
+    }
+    exchange_signal_kernel<<<1, 32, 0, s>>>(ex->d_peer_flags, ex->world, ex->rank, kFlagPitch, epoch);
+    ix->launches++;
+    ZV_CUDA(cudaGetLastError());
+    const uint8_t *b = ex->local + half;
+    int rc = launch_merge(b + nq * k * 8, b, b + nq * k * 12, block, block, block, ex->world, nq, k, out_dist, out_ids, out_counts, s,
+                          reinterpret_cast<const uint32_t *>(ex->local + ex->flags_off), kFlagPitch, epoch);
+    ix->launches++;
+    return rc;
 }
 
 }  // extern "C"

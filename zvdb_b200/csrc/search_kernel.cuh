@@ -46,6 +46,11 @@ struct SearchParams {
     uint32_t slots;          // visited-table slots (> max entries)
     uint32_t hash_words;     // words reserved for the table (>= slots)
     uint32_t cand_cap;       // entries reserved for the candidate window (>= ef, >= next_pow2(ef): reused by the final sort)
+    // Fused all-gather: when n_peers > 0 the epilogue stores this shard's top-k straight
+    // into block `rank` of every peer's gather buffer over NVLink (plain st.global on peer-mapped
+    // addresses) instead of ids/dist/counts. Block layout: ids u64[nq*k] | dist f32[nq*k] | counts u32[nq].
+    uint8_t *peer_blocks[8];
+    uint32_t n_peers;
     uint32_t *gbitmap;       // VIS_BITMAP: [gridDim.x][bm_words] visited bitmaps in global memory, all zero between queries
     uint32_t *glog;          // VIS_BITMAP: [gridDim.x][log_cap] ids whose bit is set, so the bitmap can be wiped
     uint32_t bm_words, log_cap;
@@ -417,17 +422,27 @@ search_layer0_kernel(const SearchParams p) {
     const uint32_t nres = min(np, p.k);
     for (uint32_t r = lane; r < p.k; r += 32) {
         const size_t o = static_cast<size_t>(q) * p.k + r;
+        uint64_t oid = ~0ull; float od = 0.0f;
         if (r < nres) {
             const uint64_t key = res[static_cast<uint32_t>(sorted[r])];
-            p.ids[o] = static_cast<uint64_t>(key_id(key)) * p.id_stride + p.id_base;
-            p.dist[o] = key_dist(key);
-        } else {
-            p.ids[o] = ~0ull;
-            p.dist[o] = 0.0f;
+            oid = static_cast<uint64_t>(key_id(key)) * p.id_stride + p.id_base;
+            od = key_dist(key);
+        }
+        if (p.n_peers == 0) { p.ids[o] = oid; p.dist[o] = od; }
+        else {
+            const size_t nk = static_cast<size_t>(p.nq) * p.k;
+            for (uint32_t g = 0; g < p.n_peers; ++g) {
+                reinterpret_cast<uint64_t *>(p.peer_blocks[g])[o] = oid;
+                reinterpret_cast<float *>(p.peer_blocks[g] + nk * 8)[o] = od;
+            }
         }
     }
     if (lane == 0) {
-        p.counts[q] = nres;
+        if (p.n_peers == 0) p.counts[q] = nres;
+        else {
+            const size_t nk = static_cast<size_t>(p.nq) * p.k;
+            for (uint32_t g = 0; g < p.n_peers; ++g) reinterpret_cast<uint32_t *>(p.peer_blocks[g] + nk * 12)[q] = nres;
+        }
         if (p.pops) p.pops[q] = np;
         if (p.evals) p.evals[q] = nev;
     }

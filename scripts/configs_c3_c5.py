@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[2] (C3) and configs[4] (C5) on one B200, full size, with size-independent
+parity properties checked in place (not part of pytest: minutes of GPU time). JSON lines.
+
+C3: 1M x 768 fp32 cosine, M=32, k=100: quality graph, search ef sweep, K4 exact ground truth.
+C5: 1M x 128 L2 index (reference graph + quality graph), batch sizes 1..65536 at fixed ef.
+Properties: distances non-decreasing; no duplicate ids; ids valid; search distances bit-equal to K4's
+for common (query, id); brute-force recall of itself vs a torch fp32 matmul on a sample = 1."""
+import json, sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+import zvdb_b200
+from zvdb_b200 import builder
+
+dev = torch.device("cuda", 0)
+stream = torch.cuda.current_stream().cuda_stream
+which = sys.argv[1] if len(sys.argv) > 1 else "both"
+
+
+def timed(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def check_props(ids, dist, cnt, n):
+    k = ids.shape[1]
+    mask = np.arange(k)[None, :] < cnt[:, None]
+    assert np.all(ids[mask] < n), "id out of range"
+    d = np.where(mask, dist, np.inf)
+    assert np.all(np.diff(d, axis=1) >= 0), "distances not sorted"
+    srt = np.sort(np.where(mask, ids, np.arange(k, dtype=np.uint64)[None, :] + np.uint64(1 << 40)), axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1]), "duplicate id in a result"
+
+
+if which in ("c3", "both"):
+    n, dim, nq, k, m = 1_000_000, 768, 10_000, 100, 32
+    X = np.random.default_rng(1).standard_normal((n, dim), dtype=np.float32)
+    Q = np.random.default_rng(2).standard_normal((nq, dim), dtype=np.float32)
+    h = zvdb_b200.HNSW(m, 200, metric=zvdb_b200.METRIC_COSINE)
+    t0 = time.time()
+    Xn = X / np.linalg.norm(X, axis=1, keepdims=True)
+    builder.build_quality_graph(h, Xn, m, K=64)      # candidates by L2 on normalised rows == cosine order
+    h.sync_device()
+    build_s = time.time() - t0
+    dq = torch.from_numpy(Q).to(dev)
+    d_ids = torch.empty((nq, k), dtype=torch.int64, device=dev); d_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    d_cnt = torch.empty(nq, dtype=torch.int32, device=dev); d_ev = torch.empty(nq, dtype=torch.int32, device=dev)
+    g_ids = torch.empty((nq, k), dtype=torch.int64, device=dev); g_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    g_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    bf = lambda: h.bruteforce_knn_device(dq.data_ptr(), nq, k, g_ids.data_ptr(), g_dist.data_ptr(), g_cnt.data_ptr(), stream=stream)
+    ms_bf = timed(bf, 2)
+    gt, gd, gc = g_ids.cpu().numpy().view(np.uint64), g_dist.cpu().numpy(), g_cnt.cpu().numpy().view(np.uint32)
+    check_props(gt, gd, gc, n)
+    # K4 against a torch fp32 matmul on a sample
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Xd = torch.from_numpy(Xn).to(dev)
+    ref = torch.topk(-(dq[:256] @ Xd.T), k, dim=1, largest=False).indices.cpu().numpy()
+    agree = np.mean([len(set(gt[i].tolist()) & set(ref[i].tolist())) / k for i in range(256)])
+    del Xd
+    flops = 2.0 * nq * n * dim
+    print(json.dumps({"config": "C3", "kernel": "K4 bruteforce", "n": n, "dim": dim, "nq": nq, "k": k, "metric": "cosine", "ms": ms_bf,
+                      "algorithmic_tflops": flops / ms_bf / 1e9, "issued_tflops_3xtf32": 3 * flops / ms_bf / 1e9,
+                      "agreement_with_fp32_matmul_topk_sample256": float(agree), "build_s": build_s}), flush=True)
+    for ef in (100, 128, 256, 512):
+        fn = lambda: h.search_batch_device(dq.data_ptr(), nq, k, ef, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(), 0, d_ev.data_ptr(), stream=stream)
+        ms = timed(fn, 2)
+        ids, dist, cnt = d_ids.cpu().numpy().view(np.uint64), d_dist.cpu().numpy(), d_cnt.cpu().numpy().view(np.uint32)
+        check_props(ids, dist, cnt, n)
+        rec = np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / k for i in range(nq)])
+        # bit-equal distances for (query, id) pairs both kernels returned
+        same = tot = 0
+        for i in range(0, nq, 97):
+            lut = dict(zip(gt[i].tolist(), gd[i].view(np.uint32).tolist()))
+            for j, idv in enumerate(ids[i].tolist()):
+                if idv in lut:
+                    tot += 1; same += int(lut[idv] == int(dist[i, j:j + 1].view(np.uint32)[0]))
+        ev = float(d_ev.cpu().numpy().mean())
+        print(json.dumps({"config": "C3", "kernel": "K1 search", "graph": "quality", "m": m, "ef": ef, "ms": ms, "qps": nq / ms * 1e3,
+                          "recall_at_100": float(rec), "evals_per_query": ev, "algorithmic_GBps": ev * 3072 * nq / ms / 1e6,
+                          "dist_bits_equal_to_K4": f"{same}/{tot}"}), flush=True)
+    h.deinit()
+    del X, Xn
+
+if which in ("c5", "both"):
+    n, dim, k, m, ef = 1_000_000, 128, 10, 16, 64
+    X = np.random.default_rng(1).standard_normal((n, dim), dtype=np.float32)
+    Qall = np.random.default_rng(2).standard_normal((65536, dim), dtype=np.float32)
+    for graph in ("reference", "quality"):
+        h = zvdb_b200.HNSW(m, 200)
+        if graph == "reference": h.insert_batch(X)
+        else: builder.build_quality_graph(h, X, m)
+        h.sync_device()
+        dq = torch.from_numpy(Qall).to(dev)
+        base_ids = None
+        for nq in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536):
+            d_ids = torch.empty((nq, k), dtype=torch.int64, device=dev); d_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            d_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+            fn = lambda: h.search_batch_device(dq.data_ptr(), nq, k, ef, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(), stream=stream)
+            ms = timed(fn, 5)
+            ids = d_ids.cpu().numpy()
+            if base_ids is None: base_ids = ids[0].copy()
+            assert np.array_equal(ids[0], base_ids), "result of query 0 depends on the batch size"
+            hq = Qall[:nq].copy()
+            t0 = time.perf_counter(); r = h.search_batch(hq, k, ef); e2e_ms = (time.perf_counter() - t0) * 1e3
+            print(json.dumps({"config": "C5", "graph": graph, "ef": ef, "nq": nq, "device_ms": ms, "device_qps": nq / ms * 1e3,
+                              "host_call_ms": e2e_ms, "host_call_qps": nq / e2e_ms * 1e3}), flush=True)
+        h.deinit()

@@ -73,6 +73,8 @@ struct zvdb_index {
     int num_sms = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;  // owned; used by the host-buffer entry points and uploads
+    cudaStream_t stream2 = nullptr; // owned; second lane of the chunk pipeline in zvdb_search_batch
+    cudaEvent_t bitmap_ev = nullptr; // last kernel that used the shared visited bitmaps
     float *d_arena = nullptr;       // [cap_rows][row_floats]
     uint32_t *d_adj = nullptr;      // [cap_rows][m]
     uint64_t cap_rows = 0, n_dev = 0;
@@ -186,6 +188,21 @@ static cudaError_t launch_search_wv(int metric, int cpl, const SearchParams &p, 
     }
 }
 
+// Where the exact visited set of a search with pop budget `ef` lives (see launch_search).
+static int plan_visited(const zvdb_index *ix, uint32_t ef) {
+    const HostGraph &g = ix->g;
+    const uint64_t bound = std::min<uint64_t>(g.n, 1ull + static_cast<uint64_t>(ef) * g.m);
+    const uint64_t slots = bound + bound / 4 + 16;
+    const uint64_t cand_cap = std::max<uint64_t>(2, next_pow2(ef));
+    const uint64_t smem_lists = (((static_cast<uint64_t>(ef) + 1) & ~1ull) + cand_cap) * 8 + kPoolCap * 8 + 32 * 4 + kPoolCap * 4 + 16;
+    const uint64_t smem_hash = smem_lists + slots * 4;
+    const uint64_t ctas = std::min<uint64_t>(32, (227ull * 1024) / (smem_hash + 1024));
+    int vis = (smem_hash <= ix->smem_optin && ctas >= 20) ? kVisSmemHash : kVisGlobalBitmap;
+    if (ix->visited_mode == 1) vis = kVisSmemHash;
+    if (ix->visited_mode == 2) vis = kVisGlobalBitmap;
+    return vis;
+}
+
 // Device buffers in, device buffers out, no synchronisation. Caller holds the lock and has synced
 // the device copy.
 static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t *d_ids,
@@ -217,9 +234,7 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     auto ctas_for = [](uint64_t smem) { return std::min<uint64_t>(32, (227ull * 1024) / (smem + 1024)); };
     // Where the exact visited set lives. On chip while that still leaves >= 20 warps per SM; beyond
     // that a per-CTA bitmap in global memory keeps residency up (one atomicOr per neighbour).
-    int vis = (smem_hash <= ix->smem_optin && ctas_for(smem_hash) >= 20) ? kVisSmemHash : kVisGlobalBitmap;
-    if (ix->visited_mode == 1) vis = kVisSmemHash;
-    if (ix->visited_mode == 2) vis = kVisGlobalBitmap;
+    const int vis = plan_visited(ix, ef);
     const uint64_t smem = vis == kVisSmemHash ? smem_hash : smem_lists;
     if (smem > ix->smem_optin) {
         char buf[256];
@@ -238,15 +253,19 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     if (vis == kVisGlobalBitmap) {
         const uint64_t resident = std::min<uint64_t>(ctas_for(smem), wide ? 16 : 32) * ix->num_sms;
         grid = static_cast<unsigned>(std::min<uint64_t>(nq, resident));          // persistent CTAs
+        // the bitmaps are per-CTA state shared by every launch on this handle: order launches from
+        // different streams behind the previous user
+        ZV_CUDA(cudaStreamWaitEvent(s, ix->bitmap_ev, 0));
         const uint64_t bm_words = (g.n + 31) / 32;
         const uint64_t need = grid * bm_words;
         if (need > ix->bitmap_buf.cap) {
             ZV_CUDA(ix->bitmap_buf.reserve(need));
             ZV_CUDA(cudaMemsetAsync(ix->bitmap_buf.p, 0, ix->bitmap_buf.cap * sizeof(uint32_t), s));
         }
-        ZV_CUDA(ix->vlog_buf.reserve(grid * bound));
+        const uint64_t log_cap = (bound + 3) & ~3ull;                          // 16-byte aligned logs (read back as uint4)
+        ZV_CUDA(ix->vlog_buf.reserve(grid * log_cap));
         p.gbitmap = ix->bitmap_buf.p; p.glog = ix->vlog_buf.p;
-        p.bm_words = static_cast<uint32_t>(bm_words); p.log_cap = static_cast<uint32_t>(bound);
+        p.bm_words = static_cast<uint32_t>(bm_words); p.log_cap = static_cast<uint32_t>(log_cap);
     }
     cudaError_t e;
     if (vis == kVisSmemHash) e = wide ? launch_search_wv<true, kVisSmemHash>(g.metric, cpl, p, grid, smem, s)
@@ -255,6 +274,7 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
                   : launch_search_wv<false, kVisGlobalBitmap>(g.metric, cpl, p, grid, smem, s);
     ix->launches++;
     ZV_CUDA(e);
+    if (vis == kVisGlobalBitmap) ZV_CUDA(cudaEventRecord(ix->bitmap_ev, s));
     return ZVDB_OK;
 }
 
@@ -555,6 +575,8 @@ int zvdb_create(zvdb_index **out, uint32_t dim, uint32_t m, uint32_t ef_construc
     if (dim) ix->g.fix_dim(dim);
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->bitmap_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete ix; ZV_CUDA(e); }
     *out = ix;
     return ZVDB_OK;
@@ -564,6 +586,8 @@ void zvdb_destroy(zvdb_index *ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) { cudaStreamSynchronize(ix->stream); cudaStreamDestroy(ix->stream); }
+    if (ix->stream2) { cudaStreamSynchronize(ix->stream2); cudaStreamDestroy(ix->stream2); }
+    if (ix->bitmap_ev) cudaEventDestroy(ix->bitmap_ev);
     cudaFree(ix->d_arena); cudaFree(ix->d_adj);
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
     ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_();
@@ -847,17 +871,27 @@ int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_
     ZV_CUDA(ix->cnt_buf.reserve(nq));
     if (pops) ZV_CUDA(ix->pops_buf.reserve(nq));
     if (evals) ZV_CUDA(ix->evals_buf.reserve(nq));
-    cudaStream_t s = ix->stream;
-    ZV_CUDA(cudaMemcpyAsync(ix->q_buf.p, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = launch_search(ix, ix->q_buf.p, nq, k, ef, ix->ids_buf.p, ix->dist_buf.p, ix->cnt_buf.p,
-                       pops ? ix->pops_buf.p : nullptr, evals ? ix->evals_buf.p : nullptr, 1, 0, s);
-    if (rc) return rc;
-    ZV_CUDA(cudaMemcpyAsync(ids, ix->ids_buf.p, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    ZV_CUDA(cudaMemcpyAsync(dist, ix->dist_buf.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
-    ZV_CUDA(cudaMemcpyAsync(counts, ix->cnt_buf.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (pops) ZV_CUDA(cudaMemcpyAsync(pops, ix->pops_buf.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (evals) ZV_CUDA(cudaMemcpyAsync(evals, ix->evals_buf.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    ZV_CUDA(cudaStreamSynchronize(s));
+    // Large batches whose visited sets live on chip are cut into chunks that alternate between two
+    // streams: the copy-in of chunk c+1 and the copy-out of chunk c-1 overlap the kernel of chunk c, and
+    // consecutive kernels overlap each other's tails. (Bitmap-mode launches share per-CTA state and are
+    // long compared with the copies: one chunk.)
+    const uint64_t nchunks = (nq >= 4096 && plan_visited(ix, ef) == kVisSmemHash) ? 4 : 1;
+    const uint64_t per = (nq + nchunks - 1) / nchunks;
+    for (uint64_t c = 0, off = 0; off < nq; ++c, off += per) {
+        const uint64_t cnt = std::min<uint64_t>(per, nq - off);
+        cudaStream_t s = (c & 1) ? ix->stream2 : ix->stream;
+        ZV_CUDA(cudaMemcpyAsync(ix->q_buf.p + off * dim, queries + off * dim, cnt * dim * sizeof(float), cudaMemcpyHostToDevice, s));
+        rc = launch_search(ix, ix->q_buf.p + off * dim, cnt, k, ef, ix->ids_buf.p + off * k, ix->dist_buf.p + off * k, ix->cnt_buf.p + off,
+                           pops ? ix->pops_buf.p + off : nullptr, evals ? ix->evals_buf.p + off : nullptr, 1, 0, s);
+        if (rc) return rc;
+        ZV_CUDA(cudaMemcpyAsync(ids + off * k, ix->ids_buf.p + off * k, cnt * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        ZV_CUDA(cudaMemcpyAsync(dist + off * k, ix->dist_buf.p + off * k, cnt * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+        ZV_CUDA(cudaMemcpyAsync(counts + off, ix->cnt_buf.p + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (pops) ZV_CUDA(cudaMemcpyAsync(pops + off, ix->pops_buf.p + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (evals) ZV_CUDA(cudaMemcpyAsync(evals + off, ix->evals_buf.p + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    ZV_CUDA(cudaStreamSynchronize(ix->stream));
+    if (nchunks > 1) ZV_CUDA(cudaStreamSynchronize(ix->stream2));
     return ZVDB_OK;
 }
 

@@ -370,18 +370,60 @@ search_layer0_kernel(const SearchParams p) {
                 pref_id = ns > 0 ? key_id(cand[h]) : kInvalidId;
                 pref_nb = (pref_id != kInvalidId && lane < p.m) ? __ldg(p.adj + static_cast<size_t>(pref_id) * p.m + lane) : kInvalidId;
             }
+            if constexpr (VIS == kVisGlobalBitmap) {
+                // Large-ef path: the visited test is an L2/HBM round trip (one atomicOr per neighbour), so the
+                // rows of the first U neighbours are requested TOGETHER with it instead of after it: one
+                // dependent memory trip per pop less. Rows of already-visited neighbours are fetched in vain
+                // (a few per cent on a well-connected graph); later chunks are fetched only if they hold a
+                // fresh neighbour. Results and counters are those of the compact-then-gather path.
+                const bool valid = nb != kInvalidId;
+                uint32_t old = 0;
+                if (valid) old = atomicOr(bitmap + (nb >> 5), 1u << (nb & 31));
+                const unsigned vmask = __ballot_sync(kFullMask, valid);
+                if (vmask == 0) continue;
+                const uint32_t nvalid = 32u - __clz(vmask);              // padding sits at the tail of the row
+                unsigned fmask = 0;
+                bool resolved = false;
+                auto resolve = [&]() {                                    // first use of the atomics' result
+                    const bool fresh = valid && ((old >> (nb & 31)) & 1u) == 0;         // :217, :221
+                    fmask = __ballot_sync(kFullMask, fresh);
+                    if (fresh) vlog[nev + __popc(fmask & ((1u << lane) - 1u))] = nb;
+                    nev += __popc(fmask);
+                    resolved = true;
+                };
+                // A node with one or two neighbours is usually a leaf whose neighbours were visited on the way
+                // in (the reference's near-tree): there the gather waits for the visited test after all.
+                if (nvalid <= 2) { resolve(); if (fmask == 0) continue; }
+                constexpr unsigned kChunkMask = (U == 32) ? ~0u : ((1u << U) - 1u);
+                for (uint32_t c0 = 0; c0 < nvalid; c0 += U) {
+                    if (resolved && ((fmask >> c0) & kChunkMask) == 0) continue;
+                    uint32_t ids[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t x = __shfl_sync(kFullMask, nb, c0 + u);
+                        ids[u] = x == kInvalidId ? cur : x;               // hot, valid row for the padding
+                    }
+                    const float d = rows_distance<CPL, METRIC, U>(arena, p.row_chunks, ids, qv, lane);
+                    if (!resolved) { resolve(); if (((fmask >> c0) & kChunkMask) == 0) continue; }
+                    const uint32_t j = c0 + lane / LPR;                   // the neighbour slot whose row this lane holds
+                    const uint32_t rid = __shfl_sync(kFullMask, nb, j);
+                    uint64_t key = ~0ull;
+                    if ((lane % LPR) == 0 && ((fmask >> j) & 1u)) key = pack_key(d, rid);      // :219
+                    const bool keep = key < worst;
+                    const unsigned km = __ballot_sync(kFullMask, keep);
+                    if (keep) pool[npool + __popc(km & ((1u << lane) - 1u))] = key;            // :220
+                    npool += __popc(km);
+                }
+                __syncwarp();
+            } else {
             bool fresh = false;                                  // :217, :221
-            if (nb != kInvalidId) {
-                if (VIS == kVisSmemHash) fresh = visited_insert(table, p.slots, nb);
-                else fresh = ((atomicOr(bitmap + (nb >> 5), 1u << (nb & 31)) >> (nb & 31)) & 1u) == 0;
-            }
+            if (nb != kInvalidId) fresh = visited_insert(table, p.slots, nb);
             const unsigned mask = __ballot_sync(kFullMask, fresh);
             const uint32_t t = __popc(mask);
             if (t == 0) continue;
             const uint32_t slot_t = __popc(mask & ((1u << lane) - 1u));
             if (fresh) todo[slot_t] = nb;                        // adjacency order kept
             else if (lane - slot_t + t < 32u) todo[lane - slot_t + t] = cur;   // pad todo[t..32) with a hot, valid row id
-            if (VIS == kVisGlobalBitmap) { if (fresh) vlog[nev + slot_t] = nb; }
             nev += t;
             __syncwarp();
 
@@ -409,6 +451,7 @@ search_layer0_kernel(const SearchParams p) {
                 npool += __popc(km);
             }
             __syncwarp();
+            }
         }
     }
 
@@ -448,7 +491,12 @@ search_layer0_kernel(const SearchParams p) {
     }
     if (VIS == kVisGlobalBitmap) {       // wipe exactly the words this query set, then order the wipe before the next query's atomics
         __syncwarp();
-        for (uint32_t i = lane; i < nev; i += 32) bitmap[vlog[i] >> 5] = 0u;
+        const uint32_t nev4 = nev & ~3u;                 // the log is 16-byte aligned: four ids per load
+        for (uint32_t i = lane * 4; i < nev4; i += 128) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(vlog + i);
+            bitmap[w.x >> 5] = 0u; bitmap[w.y >> 5] = 0u; bitmap[w.z >> 5] = 0u; bitmap[w.w >> 5] = 0u;
+        }
+        if (lane < nev - nev4) bitmap[vlog[nev4 + lane] >> 5] = 0u;
         __threadfence();
     }
     __syncwarp();

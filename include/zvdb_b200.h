@@ -118,6 +118,28 @@ ZVDB_API int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, ui
 ZVDB_API int zvdb_build_from_candidates(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim,
                                         const uint32_t *cand, uint32_t K, int cand_on_device);
 
+/* ---- upper layers and the descent (north_star subsystem 2) ----------------------
+ * The reference BUILDS layers >= 1 (hnsw.zig:88-108) but its search never reads them (hnsw.zig:216).
+ * With the descent switched on, a search first walks layers max_level..1 greedily from the node that
+ * first reached max_level -- on each layer the reference's own greedy walk (hnsw.zig:89-104: scan the
+ * whole list of the current node, move to a strictly closer neighbour, repeat until nothing moves;
+ * a node without the layer is not scanned, :93) -- and the node reached seeds the layer-0 search in
+ * place of entry_point. Off by default: off is the reference's search. The evals counter of a search
+ * then includes the rows the descent evaluated. */
+ZVDB_API int zvdb_set_descent(zvdb_index *ix, int on);
+ZVDB_API int64_t zvdb_descent_start(const zvdb_index *ix);   /* node where the descent starts; -1 = empty index */
+
+/* Layers >= 1 in flat form: node i has levels[i] lists of m ids (layers 1..levels[i], back to back,
+ * 0xFFFFFFFF padded at the tail) starting at list upper_base[i] (0xFFFFFFFF if levels[i] == 0), i.e.
+ * at upper_adj[upper_base[i] * m]; lists follow node order. n_lists = sum of levels.
+ * Export: every pointer may be NULL (call once with only n_lists to size the arrays). */
+ZVDB_API int zvdb_export_upper_layers(const zvdb_index *ix, uint8_t *levels, uint32_t *upper_base,
+                                      uint32_t *upper_adj, uint64_t *n_lists);
+/* Load: sets levels and the lists of layers >= 1 of an index filled by zvdb_load_graph or
+ * zvdb_build_from_candidates (which leave every node at level 0). `start` must have the maximum level. */
+ZVDB_API int zvdb_load_upper_layers(zvdb_index *ix, const uint8_t *levels, const uint32_t *upper_adj,
+                                    uint64_t n_lists, uint64_t start);
+
 /* ---- search ------------------------------------------------------------------------------ */
 
 /* HNSW(T).search(query, k), hnsw.zig:194-236: best-first from the entry point over layer 0,

@@ -70,6 +70,11 @@ def lib():
                                               i32, i32, i32, i32, C.POINTER(C.c_uint32), p,
                                               C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                               C.POINTER(C.c_uint32)]
+            pu8, pu32 = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+            g("orc_search_graph_desc").argtypes = [p, i32, sz, pu32, sz, lg, p, sz, sz, sz, i32, i32, i32, i32,
+                                                   pu8, pu32, pu32, i32, lg, pu32, p, pu32, pu32, pu32]
+            g("orc_descend_one").argtypes = [p, i32, pu8, pu32, pu32, sz, i32, lg, p, i32, pu32, p]
+            g("orc_descend_one").restype = lg
         L.orc_max_threads.restype = i32
         L.orc_distance_f32.restype = C.c_float
         L.orc_distance_f32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), i32, i32]
@@ -182,6 +187,24 @@ class OracleHNSW:
             self._f("orc_export_layer")(self.h, layer, pitch, _ptr(adj, C.c_uint32), _ptr(deg, C.c_uint32))
         return adj[:n], deg[:n]
 
+    def export_upper(self):
+        """Layers >= 1 in the flat form of zvdb_export_upper_layers: (levels[n] u8, upper_base[n] u32,
+        upper_adj[n_lists, m] u32, max_level, start) with start = the first node of maximum level."""
+        n = self.count()
+        levels = np.array([self.level(i) for i in range(n)], np.uint8)
+        base = np.full(n, 0xFFFFFFFF, np.uint32)
+        has = levels > 0
+        base[has] = (np.cumsum(levels.astype(np.uint64)) - levels)[has].astype(np.uint32)
+        nl = int(levels.astype(np.uint64).sum())
+        adj = np.full((nl, self.m), 0xFFFFFFFF, np.uint32)
+        for layer in range(1, int(levels.max(initial=0)) + 1):
+            tab, _ = self.export_layer(layer)
+            idx = np.nonzero(levels >= layer)[0]
+            adj[base[idx].astype(np.int64) + (layer - 1)] = tab[idx]
+        mx = int(levels.max(initial=0))
+        start = int(np.argmax(levels == mx)) if n else -1
+        return levels, base, adj, mx, start
+
     def search(self, query, k: int, heap_mode: int = HEAP_ZIG, dist_mode: int | None = None,
                counters: bool = False):
         """The reference call `search(query, k)` (hnsw.zig:194): (ids, distances[, pops, evals])."""
@@ -201,8 +224,10 @@ class OracleHNSW:
 
 def search_graph(points, adj, queries, ef: int, k: int | None = None, entry: int = 0,
                  dist_mode: int = DIST_SEQ, heap_mode: int = HEAP_ZIG, nthreads: int = 0,
-                 global_lock: bool = False, dtype: str = "f32"):
-    """Batched `search(q, ef)[0..k]` on a supplied padded graph. Returns dict(ids, dist, counts, pops, evals)."""
+                 global_lock: bool = False, dtype: str = "f32", upper=None):
+    """Batched `search(q, ef)[0..k]` on a supplied padded graph. Returns dict(ids, dist, counts, pops, evals).
+    upper = (levels, upper_base, upper_adj, max_level, start): first descend layers max_level..1 from
+    `start` (extension, see orc_descend in oracle_impl.h) and begin the layer-0 search where that lands."""
     npdt, ct = _NP[dtype], _CT[dtype]
     pts = np.ascontiguousarray(points, npdt)
     adj = np.ascontiguousarray(adj, np.uint32)
@@ -215,14 +240,42 @@ def search_graph(points, adj, queries, ef: int, k: int | None = None, entry: int
     pops = np.zeros(nq, np.uint32)
     evals = np.zeros(nq, np.uint32)
     n = pts.shape[0]
-    rc = getattr(lib(), f"orc_search_graph_{dtype}")(
-        _ptr(pts, ct), pts.shape[1], n, _ptr(adj, C.c_uint32), adj.shape[1] if adj.ndim == 2 else 1,
-        entry if n else -1, _ptr(q, ct), nq, ef, k, dist_mode, heap_mode, nthreads, int(global_lock),
-        _ptr(ids, C.c_uint32), _ptr(d, ct), _ptr(counts, C.c_uint32), _ptr(pops, C.c_uint32),
-        _ptr(evals, C.c_uint32))
+    if upper is not None:
+        lv, ub, ua, mx, start = upper
+        lv = np.ascontiguousarray(lv, np.uint8); ub = np.ascontiguousarray(ub, np.uint32)
+        ua = np.ascontiguousarray(ua, np.uint32)
+        if ua.size == 0:
+            ua = np.full((1, adj.shape[1]), 0xFFFFFFFF, np.uint32)
+        assert ua.shape[1] == adj.shape[1], "upper lists and layer 0 share the pitch m"
+        rc = getattr(lib(), f"orc_search_graph_desc_{dtype}")(
+            _ptr(pts, ct), pts.shape[1], n, _ptr(adj, C.c_uint32), adj.shape[1], entry if n else -1, _ptr(q, ct), nq,
+            ef, k, dist_mode, heap_mode, nthreads, int(global_lock), _ptr(lv, C.c_uint8), _ptr(ub, C.c_uint32),
+            _ptr(ua, C.c_uint32), int(mx), int(start), _ptr(ids, C.c_uint32), _ptr(d, ct), _ptr(counts, C.c_uint32),
+            _ptr(pops, C.c_uint32), _ptr(evals, C.c_uint32))
+    else:
+        rc = getattr(lib(), f"orc_search_graph_{dtype}")(
+            _ptr(pts, ct), pts.shape[1], n, _ptr(adj, C.c_uint32), adj.shape[1] if adj.ndim == 2 else 1,
+            entry if n else -1, _ptr(q, ct), nq, ef, k, dist_mode, heap_mode, nthreads, int(global_lock),
+            _ptr(ids, C.c_uint32), _ptr(d, ct), _ptr(counts, C.c_uint32), _ptr(pops, C.c_uint32),
+            _ptr(evals, C.c_uint32))
     if rc:
         raise MemoryError
     return {"ids": ids, "dist": d, "counts": counts, "pops": pops, "evals": evals}
+
+
+def descend_one(points, upper, query, dist_mode: int = DIST_SEQ, dtype: str = "f32"):
+    """Where the descent lands for one query: (node id, its distance, distance evaluations)."""
+    npdt, ct = _NP[dtype], _CT[dtype]
+    pts = np.ascontiguousarray(points, npdt)
+    q = np.ascontiguousarray(query, npdt)
+    lv, ub, ua, mx, start = upper
+    lv = np.ascontiguousarray(lv, np.uint8); ub = np.ascontiguousarray(ub, np.uint32); ua = np.ascontiguousarray(ua, np.uint32)
+    ev = C.c_uint32(0)
+    dd = ct(0)
+    node = getattr(lib(), f"orc_descend_one_{dtype}")(_ptr(pts, ct), pts.shape[1], _ptr(lv, C.c_uint8), _ptr(ub, C.c_uint32),
+                                                      _ptr(ua, C.c_uint32), ua.shape[1] if ua.ndim == 2 else 1, int(mx),
+                                                      int(start), _ptr(q, ct), dist_mode, C.byref(ev), C.byref(dd))
+    return int(node), dd.value, ev.value
 
 
 def bruteforce(points, queries, k: int, metric: int = 0, nthreads: int = 0):

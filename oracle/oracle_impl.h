@@ -374,6 +374,42 @@ static long SFX(orc_search_view)(const T *pts, int dim, size_t n, const uint32_t
     return (long)nres;
 }
 
+/* ---- descent over layers >= 1 (EXTENSION, no reference counterpart in search) ---------------
+ * zvdb's search never leaves layer 0 (hnsw.zig:216). The kernel's optional descent (K2) is stated
+ * here with the reference's own greedy walk, the loop insert runs on each layer (hnsw.zig:89-104):
+ * scan the WHOLE list of the node captured before the scan (:92,:94), move to a neighbour only if
+ * strictly closer (:97), repeat while a scan moved (:90); a node that lacks the layer is not
+ * scanned (:93). Layers are taken from max_level down to 1, starting at `start`; the node reached
+ * seeds the layer-0 search. Upper layers in flat form: node i has levels[i] lists of `m` ids
+ * (0xFFFFFFFF padded) starting at list upper_base[i]. *evals counts every distance evaluated here,
+ * the start node's included. */
+static size_t SFX(orc_descend)(const T *pts, int dim, const uint8_t *levels, const uint32_t *upper_base,
+                               const uint32_t *upper_adj, size_t m, int max_level, size_t start, const T *query,
+                               int dist_mode, uint32_t *evals, T *out_dist) {
+    size_t ep = start;
+    T curr = SFX(orc_dist)(dist_mode, query, pts + ep * dim, dim);
+    uint32_t ev = 1;
+    for (int layer = max_level; layer >= 1; --layer) {
+        int changed = 1;
+        while (changed) {
+            changed = 0;
+            const size_t cur = ep;
+            if (layer <= (int)levels[cur]) {
+                const uint32_t *list = upper_adj + ((size_t)upper_base[cur] + (size_t)(layer - 1)) * m;
+                for (size_t t = 0; t < m && list[t] != 0xFFFFFFFFu; ++t) {
+                    const uint32_t nb = list[t];
+                    const T d = SFX(orc_dist)(dist_mode, query, pts + (size_t)nb * dim, dim);
+                    ev++;
+                    if (d < curr) { ep = nb; curr = d; changed = 1; }
+                }
+            }
+        }
+    }
+    if (evals) *evals = ev;
+    if (out_dist) *out_dist = curr;
+    return ep;
+}
+
 /* Flatten layer `layer` of the index into a padded table: adj[n*pitch] (0xFFFFFFFF padding) and
  * deg[n]; nodes without that layer get degree 0. */
 static void SFX(orc_export_layer_impl)(const SFX(orc_index) *ix, int layer, size_t pitch, uint32_t *adj, uint32_t *deg) {

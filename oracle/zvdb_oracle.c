@@ -108,13 +108,16 @@
     /* Batched search(q, ef)[0..k] on a supplied padded graph (adj[n*pitch], 0xFFFFFFFF padding),     \
      * one query per OpenMP thread, read-only, no lock. nthreads <= 0: all. global_lock != 0          \
      * serialises the calls like the reference's mutex (hnsw.zig:195-196). */                         \
-    EXPORT int orc_search_graph_##S(const T *pts, int dim, size_t n, const uint32_t *adj, size_t pitch, \
+    EXPORT int orc_search_graph_desc_##S(const T *pts, int dim, size_t n, const uint32_t *adj, size_t pitch, \
                                     long entry, const T *queries, size_t nq, size_t ef, size_t k,     \
                                     int dist_mode, int heap_mode, int nthreads, int global_lock,      \
+                                    const uint8_t *levels, const uint32_t *upper_base,                \
+                                    const uint32_t *upper_adj, int max_level, long start,             \
                                     uint32_t *ids, T *d, uint32_t *counts, uint32_t *pops,            \
                                     uint32_t *evals) {                                                \
         int err = 0;                                                                                  \
         if (k > ef) k = ef;                                                                           \
+        const int descend = levels && max_level > 0 && start >= 0 && n > 0;                           \
         _Pragma("omp parallel num_threads(nthreads > 0 ? nthreads : omp_get_max_threads())")          \
         {                                                                                             \
             /* per-thread scratch (visited stamps, heap) lives across calls: a 4n-byte stamp array    \
@@ -125,14 +128,20 @@
             _Pragma("omp for schedule(dynamic, 8)")                                                   \
             for (long qi = 0; qi < (long)nq; ++qi) {                                                  \
                 long r;                                                                               \
-                uint32_t p = 0, e = 0;                                                                \
+                uint32_t p = 0, e = 0, de = 0;                                                        \
+                long en = entry;                                                                      \
+                if (descend) {                                                                        \
+                    en = (long)orc_descend_##S(pts, dim, levels, upper_base, upper_adj, pitch, max_level, \
+                                               (size_t)start, queries + (size_t)qi * dim, dist_mode, &de, NULL); \
+                    de -= 1;   /* the beam below evaluates its entry again; count that row once */    \
+                }                                                                                     \
                 if (global_lock) {                                                                    \
                     _Pragma("omp critical(orc_global_lock)")                                          \
-                    r = orc_search_view_##S(pts, dim, n, adj, NULL, pitch, 0, entry >= 0, (size_t)entry, \
+                    r = orc_search_view_##S(pts, dim, n, adj, NULL, pitch, 0, en >= 0, (size_t)en,    \
                                             queries + (size_t)qi * dim, ef, dist_mode, heap_mode, &sc, \
                                             tid, td, &p, &e);                                         \
                 } else {                                                                              \
-                    r = orc_search_view_##S(pts, dim, n, adj, NULL, pitch, 0, entry >= 0, (size_t)entry, \
+                    r = orc_search_view_##S(pts, dim, n, adj, NULL, pitch, 0, en >= 0, (size_t)en,    \
                                             queries + (size_t)qi * dim, ef, dist_mode, heap_mode, &sc, \
                                             tid, td, &p, &e);                                         \
                 }                                                                                     \
@@ -142,11 +151,27 @@
                 for (size_t j = nr; j < k; ++j) { ids[qi * k + j] = 0xFFFFFFFFu; d[qi * k + j] = (T)0; } \
                 if (counts) counts[qi] = (uint32_t)nr;                                                \
                 if (pops) pops[qi] = p;                                                               \
-                if (evals) evals[qi] = e;                                                             \
+                if (evals) evals[qi] = e + de;                                                        \
             }                                                                                         \
             free(tid); free(td);                                                                      \
         }                                                                                             \
         return err ? -1 : 0;                                                                          \
+    }                                                                                                 \
+    EXPORT int orc_search_graph_##S(const T *pts, int dim, size_t n, const uint32_t *adj, size_t pitch, \
+                                    long entry, const T *queries, size_t nq, size_t ef, size_t k,     \
+                                    int dist_mode, int heap_mode, int nthreads, int global_lock,      \
+                                    uint32_t *ids, T *d, uint32_t *counts, uint32_t *pops,            \
+                                    uint32_t *evals) {                                                \
+        return orc_search_graph_desc_##S(pts, dim, n, adj, pitch, entry, queries, nq, ef, k, dist_mode, \
+                                         heap_mode, nthreads, global_lock, NULL, NULL, NULL, 0, -1,   \
+                                         ids, d, counts, pops, evals);                                \
+    }                                                                                                 \
+    /* Where the descent lands for one query (test hook): node id, its distance, evaluations. */      \
+    EXPORT long orc_descend_one_##S(const T *pts, int dim, const uint8_t *levels, const uint32_t *upper_base, \
+                                    const uint32_t *upper_adj, size_t m, int max_level, long start,   \
+                                    const T *query, int dist_mode, uint32_t *evals, T *dist) {        \
+        return (long)orc_descend_##S(pts, dim, levels, upper_base, upper_adj, m, max_level, (size_t)start, \
+                                     query, dist_mode, evals, dist);                                  \
     }
 
 #ifndef _OPENMP

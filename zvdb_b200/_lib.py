@@ -35,6 +35,10 @@ SIGNATURES = {
     "zvdb_export_layer": (_i32, [_vp, _u32, _pu32, _pu32]),
     "zvdb_load_graph": (_i32, [_vp, _pf, _u64, _u32, _pu64, _pu32, _u64]),
     "zvdb_build_from_candidates": (_i32, [_vp, _pf, _u64, _u32, _vp, _u32, _i32]),
+    "zvdb_set_descent": (_i32, [_vp, _i32]),
+    "zvdb_descent_start": (_i64, [_vp]),
+    "zvdb_export_upper_layers": (_i32, [_vp, _vp, _vp, _vp, _pu64]),
+    "zvdb_load_upper_layers": (_i32, [_vp, _vp, _vp, _u64, _u64]),
     "zvdb_search": (_i32, [_vp, _pf, _u32, _u32, _pu64, _pf, _pu32]),
     "zvdb_search_batch": (_i32, [_vp, _vp, _u64, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "zvdb_search_batch_device": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp]),

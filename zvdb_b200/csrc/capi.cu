@@ -85,6 +85,12 @@ struct zvdb_index {
     DevBuf<float> bf_xhi, bf_xlo, bf_xnorm, bf_qhi, bf_qlo;
     DevBuf<uint64_t> bf_part, bf_glists;
     uint64_t bf_rows = 0;           // rows covered by bf_xhi/bf_xlo (0 = stale)
+    // K2 (descent): flat copy of layers >= 1, refreshed when the host's upper_version moves
+    DevBuf<uint8_t> d_level;
+    DevBuf<uint32_t> d_upper_base, d_upper_adj;
+    DevBuf<uint4> seeds_buf;        // per-query output of descend_kernel
+    uint64_t upper_uploaded = ~0ull;
+    bool descent = false;           // off = the reference's search (entry_point, layer 0 only)
     uint32_t variant = 0;           // 0 automatic, 1 narrow, 2 wide (tuning/testing)
     uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap
     std::atomic<uint64_t> launches{0};
@@ -154,6 +160,31 @@ static int sync_device_locked(zvdb_index *ix) {
     return ZVDB_OK;
 }
 
+// Device copy of layers >= 1 for the descent (K2): levels[n], upper_base[n], upper_adj[n_lists][m].
+// Re-sent whole whenever a list above layer 0 changed (half the nodes have one; the reference links
+// one neighbour per layer and insert, hnsw.zig:106-108).
+static int sync_upper_locked(zvdb_index *ix) {
+    HostGraph &g = ix->g;
+    if (!ix->descent || g.n == 0 || g.max_level == 0) return ZVDB_OK;
+    if (ix->upper_uploaded == g.upper_version) return ZVDB_OK;
+    const uint64_t lists = g.upper_lists();
+    if (lists >= 0xFFFFFFFFull) return fail(ZVDB_ERR_UNSUPPORTED, "descent: more than 2^32-1 upper-layer lists");
+    std::vector<uint32_t> base, adj;
+    try { base.resize(g.n); adj.resize(std::max<uint64_t>(1, lists * g.m)); }
+    catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "descent: out of memory"); }
+    g.flatten_upper(base.data(), adj.data());
+    ZV_CUDA(cudaSetDevice(ix->device));
+    ZV_CUDA(ix->d_level.reserve(g.n));
+    ZV_CUDA(ix->d_upper_base.reserve(g.n));
+    ZV_CUDA(ix->d_upper_adj.reserve(adj.size()));
+    ZV_CUDA(cudaMemcpyAsync(ix->d_level.p, g.level.data(), g.n, cudaMemcpyHostToDevice, ix->stream));
+    ZV_CUDA(cudaMemcpyAsync(ix->d_upper_base.p, base.data(), g.n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+    ZV_CUDA(cudaMemcpyAsync(ix->d_upper_adj.p, adj.data(), adj.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+    ZV_CUDA(cudaStreamSynchronize(ix->stream));
+    ix->upper_uploaded = g.upper_version;
+    return ZVDB_OK;
+}
+
 // ---- K1 launch ------------------------------------------------------------------------------
 
 template <int CPL, int METRIC, bool WIDE, int VIS>
@@ -185,6 +216,26 @@ static cudaError_t launch_search_wv(int metric, int cpl, const SearchParams &p, 
         case 0: return launch_search_metric<kMetricL2, WIDE, VIS>(cpl, p, grid, smem, s);
         case 1: return launch_search_metric<kMetricCos, WIDE, VIS>(cpl, p, grid, smem, s);
         default: return launch_search_metric<kMetricDot, WIDE, VIS>(cpl, p, grid, smem, s);
+    }
+}
+
+template <int METRIC>
+static cudaError_t launch_descend_metric(int cpl, const SearchParams &p, unsigned grid, cudaStream_t s) {
+    switch (cpl) {
+        case 1: descend_kernel<1, METRIC><<<grid, 128, 0, s>>>(p); break;
+        case 2: descend_kernel<2, METRIC><<<grid, 128, 0, s>>>(p); break;
+        case 4: descend_kernel<4, METRIC><<<grid, 128, 0, s>>>(p); break;
+        case 6: descend_kernel<6, METRIC><<<grid, 128, 0, s>>>(p); break;
+        case 8: descend_kernel<8, METRIC><<<grid, 128, 0, s>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+static cudaError_t launch_descend(int metric, int cpl, const SearchParams &p, unsigned grid, cudaStream_t s) {
+    switch (metric) {
+        case 0: return launch_descend_metric<kMetricL2>(cpl, p, grid, s);
+        case 1: return launch_descend_metric<kMetricCos>(cpl, p, grid, s);
+        default: return launch_descend_metric<kMetricDot>(cpl, p, grid, s);
     }
 }
 
@@ -222,6 +273,17 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     p.row_chunks = g.row_floats / 4;
     p.m = g.m; p.n = static_cast<uint32_t>(g.n); p.entry = static_cast<uint32_t>(g.entry); p.dim = g.dim;
     p.nq = static_cast<uint32_t>(nq); p.k = k; p.ef = ef;
+    if (ix->descent && g.max_level > 0) {                 // K2: start at the top node, walk down, then the beam
+        int rcu = sync_upper_locked(ix);
+        if (rcu) return rcu;
+        p.levels = ix->d_level.p; p.upper_base = ix->d_upper_base.p; p.upper_adj = ix->d_upper_adj.p;
+        p.max_level = g.max_level; p.descent_start = static_cast<uint32_t>(g.top_node);
+        if (nq > ix->seeds_buf.cap) {                     // grown behind whatever still reads the old one
+            ZV_CUDA(cudaDeviceSynchronize());
+            ZV_CUDA(ix->seeds_buf.reserve(nq));
+        }
+        p.seeds = ix->seeds_buf.p;
+    }
     const uint32_t chunks_per_lane = (p.row_chunks + 31) / 32;
     if (chunks_per_lane > 8) return fail(ZVDB_ERR_UNSUPPORTED, "dim > 1024 is not built into the search kernel");
     const int cpl = chunks_per_lane <= 1 ? 1 : chunks_per_lane <= 2 ? 2 : chunks_per_lane <= 4 ? 4 : chunks_per_lane <= 6 ? 6 : 8;
@@ -268,13 +330,20 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
         p.bm_words = static_cast<uint32_t>(bm_words); p.log_cap = static_cast<uint32_t>(log_cap);
     }
     cudaError_t e;
+    if (p.seeds) {                                        // K2 first: one warp per query, 4 per CTA
+        // the seeds are per-handle scratch like the bitmaps: order launches from different streams
+        if (vis != kVisGlobalBitmap) ZV_CUDA(cudaStreamWaitEvent(s, ix->bitmap_ev, 0));
+        e = launch_descend(g.metric, cpl, p, static_cast<unsigned>((nq + 3) / 4), s);
+        ix->launches++;
+        ZV_CUDA(e);
+    }
     if (vis == kVisSmemHash) e = wide ? launch_search_wv<true, kVisSmemHash>(g.metric, cpl, p, grid, smem, s)
                                       : launch_search_wv<false, kVisSmemHash>(g.metric, cpl, p, grid, smem, s);
     else e = wide ? launch_search_wv<true, kVisGlobalBitmap>(g.metric, cpl, p, grid, smem, s)
                   : launch_search_wv<false, kVisGlobalBitmap>(g.metric, cpl, p, grid, smem, s);
     ix->launches++;
     ZV_CUDA(e);
-    if (vis == kVisGlobalBitmap) ZV_CUDA(cudaEventRecord(ix->bitmap_ev, s));
+    if (vis == kVisGlobalBitmap || p.seeds) ZV_CUDA(cudaEventRecord(ix->bitmap_ev, s));
     return ZVDB_OK;
 }
 
@@ -591,6 +660,7 @@ void zvdb_destroy(zvdb_index *ix) {
     cudaFree(ix->d_arena); cudaFree(ix->d_adj);
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
     ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_();
+    ix->d_level.free_(); ix->d_upper_base.free_(); ix->d_upper_adj.free_(); ix->seeds_buf.free_();
     ix->bf_xhi.free_(); ix->bf_xlo.free_(); ix->bf_xnorm.free_(); ix->bf_qhi.free_(); ix->bf_qlo.free_(); ix->bf_part.free_(); ix->bf_glists.free_();
     delete ix;
 }
@@ -736,6 +806,68 @@ int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t di
         const uint64_t b = offsets[i], e = offsets[i + 1];
         for (uint64_t t = b; t < e; ++t) g.adj0[i * g.m + (t - b)] = nbrs[t];
     }
+    return ZVDB_OK;
+}
+
+int zvdb_set_descent(zvdb_index *ix, int on) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->descent = on != 0;
+    return ZVDB_OK;
+}
+
+int64_t zvdb_descent_start(const zvdb_index *ix) { return (ix && ix->g.has_entry) ? static_cast<int64_t>(ix->g.top_node) : -1; }
+
+int zvdb_load_upper_layers(zvdb_index *ix, const uint8_t *levels, const uint32_t *upper_adj, uint64_t n_lists, uint64_t start) {
+    if (!ix || !levels || (n_lists && !upper_adj)) return fail(ZVDB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    HostGraph &g = ix->g;
+    if (g.n == 0) return n_lists ? fail(ZVDB_ERR_INVALID, "load_upper_layers: empty index") : ZVDB_OK;
+    if (start >= g.n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "load_upper_layers: start node out of range");
+    uint64_t total = 0; uint32_t mx = 0;
+    for (uint64_t i = 0; i < g.n; ++i) {
+        if (levels[i] > 31) return fail(ZVDB_ERR_INVALID, "load_upper_layers: level > 31 (hnsw.zig:174)");
+        total += levels[i]; mx = std::max<uint32_t>(mx, levels[i]);
+    }
+    if (total != n_lists) return fail(ZVDB_ERR_INVALID, "load_upper_layers: n_lists != sum of levels");
+    if (levels[start] != mx) return fail(ZVDB_ERR_INVALID, "load_upper_layers: the start node must have the maximum level");
+    for (uint64_t e = 0; e < n_lists * g.m; ++e)
+        if (upper_adj[e] != kInvalidId && upper_adj[e] >= g.n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "load_upper_layers: neighbour id out of range");
+    try {
+        g.level.assign(levels, levels + g.n);
+        g.upper_off.assign(g.n, ~0ull);
+        g.upper.clear();
+        g.upper.reserve(total * (g.m + 1));
+        uint64_t at = 0;
+        for (uint64_t i = 0; i < g.n; ++i) {
+            const uint32_t lv = levels[i];
+            if (!lv) continue;
+            g.upper_off[i] = g.upper.size();
+            for (uint32_t l = 0; l < lv; ++l) {                    // list lengths first (padding sits at the tail)
+                const uint32_t *list = upper_adj + (at + l) * g.m;
+                uint32_t c = 0;
+                while (c < g.m && list[c] != kInvalidId) ++c;
+                for (uint32_t t = c; t < g.m; ++t)
+                    if (list[t] != kInvalidId) return fail(ZVDB_ERR_INVALID, "load_upper_layers: padding inside a list");
+                g.upper.push_back(c);
+            }
+            g.upper.insert(g.upper.end(), upper_adj + at * g.m, upper_adj + (at + lv) * g.m);
+            at += lv;
+        }
+    } catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "out of memory"); }
+    g.max_level = mx; g.top_node = start; ++g.upper_version;
+    return ZVDB_OK;
+}
+
+int zvdb_export_upper_layers(const zvdb_index *cix, uint8_t *levels, uint32_t *upper_base, uint32_t *upper_adj, uint64_t *n_lists) {
+    if (!cix) return fail(ZVDB_ERR_INVALID, "null index");
+    zvdb_index *ix = const_cast<zvdb_index *>(cix);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const HostGraph &g = ix->g;
+    if (n_lists) *n_lists = g.upper_lists();
+    if (levels && g.n) std::memcpy(levels, g.level.data(), g.n);
+    if (upper_base && upper_adj) g.flatten_upper(upper_base, upper_adj);
+    else if (upper_base || upper_adj) return fail(ZVDB_ERR_INVALID, "export_upper_layers: upper_base and upper_adj go together");
     return ZVDB_OK;
 }
 

@@ -37,6 +37,8 @@ struct HostGraph {
     bool has_entry = false;         // entry_point: ?usize, hnsw.zig:46
     uint64_t entry = 0;
     uint32_t max_level = 0;         // hnsw.zig:47
+    uint64_t top_node = 0;          // first node that reached max_level: where the descent (K2) starts
+    uint64_t upper_version = 0;     // bumped whenever a list of a layer >= 1 (or a node level) changes
     uint64_t rng = 0x243F6A8885A308D3ull;
 
     // what the device copy has not seen yet
@@ -54,7 +56,7 @@ struct HostGraph {
     void reset_nodes() {
         release();
         n = 0; adj0.clear(); level.clear(); upper_off.clear(); upper.clear();
-        has_entry = false; entry = 0; max_level = 0;
+        has_entry = false; entry = 0; max_level = 0; top_node = 0; ++upper_version;
         rows_uploaded = 0; dirty.clear(); adj_all_dirty = true;
     }
 
@@ -138,7 +140,7 @@ struct HostGraph {
             }
             std::memcpy(list, tmp.data(), static_cast<size_t>(m) * sizeof(uint32_t));
         }
-        if (layer == 0) mark_dirty(node);
+        if (layer == 0) mark_dirty(node); else ++upper_version;
     }
 
     // Remember that `node`'s layer-0 row must be re-sent; past a quarter of the table a whole-table
@@ -165,6 +167,7 @@ struct HostGraph {
             adj0.resize((id + 1) * m, kInvalidId);
             level.push_back(static_cast<uint8_t>(lv));
             if (lv > 0) {
+                ++upper_version;
                 upper_off.push_back(upper.size());
                 upper.resize(upper.size() + lv, 0u);
                 upper.resize(upper.size() + static_cast<size_t>(lv) * m, kInvalidId);
@@ -216,8 +219,27 @@ struct HostGraph {
             has_entry = true;                                                    // only for id 0, :110-112
             entry = id;
         }
-        if (lv > max_level) max_level = lv;                                      // after the loop, :114-116
+        if (lv > max_level) { max_level = lv; top_node = id; }                   // after the loop, :114-116
         return 0;
+    }
+
+    // Layers >= 1 in the flat form the device (and zvdb_export_upper_layers) uses: node i has level[i]
+    // lists of m ids (layers 1..level[i], back to back, kInvalidId padded) starting at list base[i].
+    uint64_t upper_lists() const {
+        uint64_t t = 0;
+        for (uint64_t i = 0; i < n; ++i) t += level[i];
+        return t;
+    }
+    void flatten_upper(uint32_t *base, uint32_t *adj) const {
+        uint64_t at = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint32_t lv = level[i];
+            base[i] = lv ? static_cast<uint32_t>(at) : kInvalidId;
+            if (lv) {
+                std::memcpy(adj + at * m, upper.data() + upper_off[i] + lv, static_cast<size_t>(lv) * m * sizeof(uint32_t));
+                at += lv;
+            }
+        }
     }
 };
 

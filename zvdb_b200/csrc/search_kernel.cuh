@@ -51,6 +51,16 @@ struct SearchParams {
     // addresses) instead of ids/dist/counts. Block layout: ids u64[nq*k] | dist f32[nq*k] | counts u32[nq].
     uint8_t *peer_blocks[8];
     uint32_t n_peers;
+    // K2, upper-layer descent (north_star subsystem 2). levels == null is the
+    // reference's search, which never reads a layer above 0 (hnsw.zig:216). Layout: node i has
+    // levels[i] lists of m ids (layers 1..levels[i], back to back) starting at list upper_base[i].
+    const uint8_t *levels;       // [n]
+    const uint32_t *upper_base;  // [n]
+    const uint32_t *upper_adj;   // [n_lists][m], kInvalidId padded
+    uint32_t max_level, descent_start;
+    // written by descend_kernel, read by search_layer0_kernel: per query (node reached, its distance bits,
+    // rows the descent evaluated beyond its start node, 0); null = start every query at `entry`
+    uint4 *seeds;
     uint32_t *gbitmap;       // VIS_BITMAP: [gridDim.x][bm_words] visited bitmaps in global memory, all zero between queries
     uint32_t *glog;          // VIS_BITMAP: [gridDim.x][log_cap] ids whose bit is set, so the bitmap can be wiped
     uint32_t bm_words, log_cap;
@@ -267,6 +277,71 @@ __device__ __forceinline__ uint32_t merge_pool(uint64_t *win, uint32_t ns, uint3
     return min(ns + npool, cap);
 }
 
+// K2: greedy descent over layers max_level..1, one warp per query (extension; not launched in parity
+// mode). The walk on one layer is the reference's own greedy walk, the one insert runs on every layer
+// (hnsw.zig:89-104): scan the WHOLE list of the node captured before the scan, move to a neighbour
+// only if it is strictly closer; after the scan the walker stands on the first minimum of the list (if
+// that beats where it stood); repeat until a scan moves nothing. A node that does not have the layer is
+// not scanned (:93). Here the layers are taken top down and the node reached on layer 1 seeds the
+// layer-0 beam of search_layer0_kernel instead of entry_point. A kernel of its own so that the beam's
+// register budget (64 per thread, 32 warps per SM) is untouched.
+template <int CPL, int METRIC>
+__global__ void __launch_bounds__(128) descend_kernel(const SearchParams p) {
+    constexpr int U = Unroll<CPL, false>::value;
+    constexpr uint32_t LPR = 32 / U;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= p.nq) return;
+    const float4 *__restrict__ arena = p.arena;
+    Chunk2 qv[CPL];
+    {
+        const float *qp = p.queries + static_cast<size_t>(q) * p.dim;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const uint32_t i = (lane + 32u * c) * 4u;
+            const float x = i + 0 < p.dim ? qp[i + 0] : 0.f, y = i + 1 < p.dim ? qp[i + 1] : 0.f;
+            const float z = i + 2 < p.dim ? qp[i + 2] : 0.f, w = i + 3 < p.dim ? qp[i + 3] : 0.f;
+            qv[c].xy = pack2(x, y); qv[c].zw = pack2(z, w);
+        }
+    }
+    uint32_t entry = p.descent_start, ndesc = 0;
+    float d0 = row_distance<CPL, METRIC>(arena, p.row_chunks, entry, qv, lane);
+    for (uint32_t layer = p.max_level; layer >= 1; --layer) {
+        for (;;) {
+            if (layer > __ldg(p.levels + entry)) break;                                           // :93
+            const uint32_t *list = p.upper_adj + (static_cast<size_t>(__ldg(p.upper_base + entry)) + layer - 1) * p.m;
+            uint64_t best = ~0ull;                               // (ordered distance, position in the list)
+            for (uint32_t base = 0; base < p.m; base += 32) {
+                const uint32_t nb = (base + lane < p.m) ? __ldg(list + base + lane) : kInvalidId;
+                const unsigned vmask = __ballot_sync(kFullMask, nb != kInvalidId);
+                if (vmask == 0) break;
+                const uint32_t nvalid = 32u - __clz(vmask);
+                for (uint32_t c0 = 0; c0 < nvalid; c0 += U) {
+                    uint32_t ids[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t x = __shfl_sync(kFullMask, nb, (c0 + u) & 31);
+                        ids[u] = x == kInvalidId ? entry : x;
+                    }
+                    const float d = rows_distance<CPL, METRIC, U>(arena, p.row_chunks, ids, qv, lane);
+                    const uint32_t j = c0 + lane / LPR;
+                    if ((lane % LPR) == 0 && j < nvalid)
+                        best = min(best, (static_cast<uint64_t>(float_to_ordered(d)) << 32) | (base + j));
+                }
+                ndesc += nvalid;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) best = min(best, shfl_xor_u64(best, off));
+            if (best == ~0ull) break;
+            const float bd = ordered_to_float(static_cast<uint32_t>(best >> 32));
+            if (!(bd < d0)) break;                                                                // strict <, :97
+            entry = __ldg(list + static_cast<uint32_t>(best));
+            d0 = bd;                                                                              // changed = true, :98-100
+        }
+    }
+    if (lane == 0) p.seeds[q] = make_uint4(entry, __float_as_uint(d0), ndesc, 0u);
+}
+
 enum : int { kVisSmemHash = 0, kVisGlobalBitmap = 1 };
 
 // VIS selects the exact visited set:
@@ -315,11 +390,18 @@ search_layer0_kernel(const SearchParams p) {
     // hnsw.zig:208-209: push the entry point, mark it visited
     uint32_t np = 0, h = 0, ns = 0, npool = 1, nev = 1;   // pops, window start, window length, pool fill, evaluations
     {
-        const float d0 = row_distance<CPL, METRIC>(arena, p.row_chunks, p.entry, qv, lane);
+        uint32_t entry = p.entry;
+        float d0;
+        if (p.seeds == nullptr) {
+            d0 = row_distance<CPL, METRIC>(arena, p.row_chunks, entry, qv, lane);
+        } else {                                           // K2 ran first: start where the descent landed
+            const uint4 sd = __ldg(p.seeds + q);
+            entry = sd.x; d0 = __uint_as_float(sd.y);
+        }
         if (lane == 0) {
-            pool[0] = pack_key(d0, p.entry);
-            if (VIS == kVisSmemHash) visited_insert(table, p.slots, p.entry);
-            else { atomicOr(bitmap + (p.entry >> 5), 1u << (p.entry & 31)); vlog[0] = p.entry; }
+            pool[0] = pack_key(d0, entry);
+            if (VIS == kVisSmemHash) visited_insert(table, p.slots, entry);
+            else { atomicOr(bitmap + (entry >> 5), 1u << (entry & 31)); vlog[0] = entry; }
         }
     }
     uint64_t worst = ~0ull;            // largest key of a FULL window: worse pushes can never be popped
@@ -487,7 +569,7 @@ search_layer0_kernel(const SearchParams p) {
             for (uint32_t g = 0; g < p.n_peers; ++g) reinterpret_cast<uint32_t *>(p.peer_blocks[g] + nk * 12)[q] = nres;
         }
         if (p.pops) p.pops[q] = np;
-        if (p.evals) p.evals[q] = nev;
+        if (p.evals) p.evals[q] = nev + (p.seeds ? __ldg(p.seeds + q).z : 0u);
     }
     if (VIS == kVisGlobalBitmap) {       // wipe exactly the words this query set, then order the wipe before the next query's atomics
         __syncwarp();

@@ -179,6 +179,33 @@ class HNSW:
             L.check(L.lib().zvdb_build_from_candidates(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.shape[0],
                                                        p.shape[1], c.ctypes.data, c.shape[1], 0))
 
+    # -- upper layers and the descent (K2; extension, off = the reference's search) ----------------
+    def set_descent(self, on: bool = True) -> None:
+        """Walk layers max_level..1 greedily before the layer-0 search (zvdb_set_descent)."""
+        L.check(L.lib().zvdb_set_descent(self._h, 1 if on else 0))
+
+    @property
+    def descent_start(self) -> Optional[int]:
+        e = int(L.lib().zvdb_descent_start(self._h))
+        return None if e < 0 else e
+
+    def export_upper_layers(self):
+        """(levels[n] u8, upper_base[n] u32, upper_adj[n_lists, m] u32) of layers >= 1, flat form."""
+        n = self.count()
+        nl = C.c_uint64(0)
+        L.check(L.lib().zvdb_export_upper_layers(self._h, None, None, None, C.byref(nl)))
+        levels = np.zeros(max(n, 1), np.uint8)
+        base = np.full(max(n, 1), 0xFFFFFFFF, np.uint32)
+        adj = np.full((max(nl.value, 1), self.m), 0xFFFFFFFF, np.uint32)
+        L.check(L.lib().zvdb_export_upper_layers(self._h, levels.ctypes.data, base.ctypes.data, adj.ctypes.data, C.byref(nl)))
+        return levels[:n], base[:n], adj[:nl.value]
+
+    def load_upper_layers(self, levels, upper_adj, start: int) -> None:
+        """Set node levels and the lists of layers >= 1 (flat form, node order) of a loaded graph."""
+        lv = np.ascontiguousarray(levels, np.uint8)
+        adj = np.ascontiguousarray(upper_adj, np.uint32).reshape(-1, self.m) if len(upper_adj) else np.zeros((0, self.m), np.uint32)
+        L.check(L.lib().zvdb_load_upper_layers(self._h, lv.ctypes.data, adj.ctypes.data if adj.size else None, adj.shape[0], start))
+
     # -- search (hnsw.zig:194) -------------------------------------------------------------------
     def search(self, query: Sequence[float], k: int) -> list:
         """`search(query, k)`: list of Node, len = min(k, reachable); empty index -> []."""

@@ -23,8 +23,13 @@
 //                           against the thread's running k-th best, rare insertion into a sorted
 //                           per-thread list (shared memory; global memory when k is large).
 //                           The score matrix never exists in memory.
-// A work item is (query tile, row split); each item leaves a sorted candidate list per query. A
-// second small kernel merges the splits, RE-COMPUTES the distance of the best k+slack candidates
+// Work is cut into SEGMENTS (query tile, row-tile range, result slot) laid out by the host
+// (plan_segments in capi.cu): whole waves of equal segments, one per CTA, sweeping the same rows at
+// the same time (every X tile is then shared through L2 by all CTAs), and a last wave whose leftover
+// segments are cut finer so that all CTAs finish together. Few, long segments matter: every segment
+// starts with an empty candidate list and pays ~kp*ln(rows/kp) list insertions per query to warm
+// its threshold up. Each segment leaves a sorted candidate list per query in its slot. A
+// second small kernel merges the slots, RE-COMPUTES the distance of the best k+slack candidates
 // exactly (difference form, the same summation order as the search kernel, so both kernels return
 // bit-identical distances for the same (query, id)), orders by (distance, id) and writes k.
 #pragma once
@@ -47,10 +52,12 @@ constexpr uint32_t kMaxStages = 3;
 
 struct BfParams {
     const float *xnorm;      // [n] squared row norms (L2 only)
-    uint64_t *part_keys;     // [n_splits][nq][kp] sorted candidate keys per (split, query)
+    uint64_t *part_keys;     // [n_slots][nq][kp] sorted candidate keys per (slot, query); ~0 where a slot is unused
     uint64_t *glists;        // [gridDim.x][kp][128] per-thread lists when they do not fit in smem, else null
+    const uint4 *segs;       // segments (query tile, first row tile, end row tile, slot), grouped by CTA
+    const uint32_t *seg_off; // [gridDim.x + 1] CTA b owns segs[seg_off[b] .. seg_off[b+1])
     uint32_t n, nq, kchunks, kp;
-    uint32_t n_qtiles, n_splits, tiles_per_split, n_rtiles, stages, metric;
+    uint32_t n_slots, stages, metric;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -114,21 +121,39 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // Instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = 128.
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kBN >> 3) << 17) | ((kBM >> 4) << 24);
 
-// Sorted insertion into this thread's candidate list (ascending keys, stride 128 entries between
-// positions so the 128 epilogue threads interleave). Returns the new threshold distance.
-__device__ __noinline__ float list_insert(uint64_t *L, uint32_t kp, uint64_t key) {
+// This thread's candidate list: kp ascending keys, 128 entries apart (the 128 epilogue threads
+// interleave). GL = false: in shared memory, addressed as such (ld/st.shared, not generic);
+// GL = true: in global memory (k too large for shared memory).
+template <bool GL>
+struct CandList {
+    uint64_t *g; uint32_t s;
+    __device__ __forceinline__ uint64_t get(uint32_t i) const {
+        if (GL) return g[static_cast<size_t>(i) * 128];
+        uint64_t v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(s + i * 1024u) : "memory"); return v;
+    }
+    __device__ __forceinline__ void put(uint32_t i, uint64_t v) const {
+        if (GL) { g[static_cast<size_t>(i) * 128] = v; return; }
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(s + i * 1024u), "l"(v) : "memory");
+    }
+};
+
+// Sorted insertion (ascending keys). Returns the new threshold distance. Kept out of line: it is the
+// rare path and must not cost the tile loop registers.
+template <bool GL>
+__device__ __noinline__ float list_insert(const CandList<GL> L, uint32_t kp, uint64_t key) {
     uint32_t pos = kp - 1;
     while (pos > 0) {
-        const uint64_t prev = L[static_cast<size_t>(pos - 1) * 128];
+        const uint64_t prev = L.get(pos - 1);
         if (prev <= key) break;
-        L[static_cast<size_t>(pos) * 128] = prev;
+        L.put(pos, prev);
         --pos;
     }
-    L[static_cast<size_t>(pos) * 128] = key;
-    const uint64_t worst = L[static_cast<size_t>(kp - 1) * 128];
+    L.put(pos, key);
+    const uint64_t worst = L.get(kp - 1);
     return worst == ~0ull ? __int_as_float(0x7f800000) : key_dist(worst);
 }
 
+template <bool GL>
 __global__ void __launch_bounds__(kThreads, 1)
 bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                     const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
@@ -156,15 +181,15 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t n_items = p.n_qtiles * p.n_splits;
+    const uint32_t seg_begin = __ldg(p.seg_off + blockIdx.x), seg_end = __ldg(p.seg_off + blockIdx.x + 1);
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const uint32_t split = item / p.n_qtiles, qt = item % p.n_qtiles;
-                const uint32_t t0 = split * p.tiles_per_split, t1 = min(p.n_rtiles, t0 + p.tiles_per_split);
+            for (uint32_t si = seg_begin; si < seg_end; ++si) {
+                const uint4 sg = __ldg(p.segs + si);
+                const uint32_t qt = sg.x, t0 = sg.y, t1 = sg.z;
                 for (uint32_t t = t0; t < t1; ++t) {
                     for (uint32_t kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(empty + stage, phase ^ 1);
@@ -184,9 +209,9 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, tile_count = 0;
-            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const uint32_t split = item / p.n_qtiles;
-                const uint32_t t0 = split * p.tiles_per_split, t1 = min(p.n_rtiles, t0 + p.tiles_per_split);
+            for (uint32_t si = seg_begin; si < seg_end; ++si) {
+                const uint4 sg = __ldg(p.segs + si);
+                const uint32_t t0 = sg.y, t1 = sg.z;
                 for (uint32_t t = t0; t < t1; ++t, ++tile_count) {
                     const uint32_t buf = tile_count & 1, use = tile_count >> 1;
                     mbar_wait(tempty + buf, (use & 1) ^ 1);          // epilogue drained this accumulator
@@ -216,14 +241,16 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
         // ===== epilogue: 4 warps, thread = one query of the tile = one TMEM lane =====
         const uint32_t wq = warp & 3;                                // TMEM lane quarter this warp may read
         const uint32_t et = wq * 32 + lane;                          // query row in the tile
-        uint64_t *L = p.glists ? p.glists + static_cast<size_t>(blockIdx.x) * p.kp * 128 + et : lists_s + et;
+        CandList<GL> L;
+        L.g = GL ? p.glists + static_cast<size_t>(blockIdx.x) * p.kp * 128 + et : nullptr;
+        L.s = smem_u32(lists_s + et);
         const float scale = p.metric == kMetricL2 ? -2.0f : -1.0f;
         const float inf = __int_as_float(0x7f800000);
         uint32_t tile_count = 0;
-        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const uint32_t split = item / p.n_qtiles, qt = item % p.n_qtiles;
-            const uint32_t t0 = split * p.tiles_per_split, t1 = min(p.n_rtiles, t0 + p.tiles_per_split);
-            for (uint32_t i = 0; i < p.kp; ++i) L[static_cast<size_t>(i) * 128] = ~0ull;
+        for (uint32_t si = seg_begin; si < seg_end; ++si) {
+            const uint4 sg = __ldg(p.segs + si);
+            const uint32_t qt = sg.x, t0 = sg.y, t1 = sg.z, slot = sg.w;
+            for (uint32_t i = 0; i < p.kp; ++i) L.put(i, ~0ull);
             float tau = inf;
             for (uint32_t t = t0; t < t1; ++t, ++tile_count) {
                 const uint32_t buf = tile_count & 1, use = tile_count >> 1;
@@ -256,7 +283,7 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             // rows arrive in ascending id order, so on an exact tie the earlier id stays: strict <
-                            if (d[j] < tau) tau = list_insert(L, p.kp, pack_key(d[j], row0 + c * 32 + j));
+                            if (d[j] < tau) tau = list_insert<GL>(L, p.kp, pack_key(d[j], row0 + c * 32 + j));
                         }
                     }
                 }
@@ -266,8 +293,8 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
             }
             const uint32_t q = qt * kBM + et;
             if (q < p.nq) {
-                uint64_t *out = p.part_keys + (static_cast<size_t>(split) * p.nq + q) * p.kp;
-                for (uint32_t i = 0; i < p.kp; ++i) out[i] = L[static_cast<size_t>(i) * 128];
+                uint64_t *out = p.part_keys + (static_cast<size_t>(slot) * p.nq + q) * p.kp;
+                for (uint32_t i = 0; i < p.kp; ++i) out[i] = L.get(i);
             }
         }
     }
@@ -309,7 +336,7 @@ __global__ void split_tf32_kernel(const float *__restrict__ src, uint32_t src_pi
 struct BfFinalParams {
     const float4 *arena;
     const float *queries;      // [nq][dim]
-    const uint64_t *part_keys; // [n_splits][nq][kp]
+    const uint64_t *part_keys; // [n_splits][nq][kp]  (n_splits = result slots per query; unused ones hold ~0)
     uint64_t *ids;             // [nq][k]
     float *dist;               // [nq][k]
     uint32_t *counts;          // [nq]

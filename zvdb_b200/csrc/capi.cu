@@ -84,6 +84,8 @@ struct zvdb_index {
     // K4 (brute force): TF32 hi/lo split of the arena + squared row norms, rebuilt when the rows change
     DevBuf<float> bf_xhi, bf_xlo, bf_xnorm, bf_qhi, bf_qlo;
     DevBuf<uint64_t> bf_part, bf_glists;
+    DevBuf<uint4> bf_segs;
+    DevBuf<uint32_t> bf_seg_off;
     uint64_t bf_rows = 0;           // rows covered by bf_xhi/bf_xlo (0 = stale)
     // K2 (descent): flat copy of layers >= 1, refreshed when the host's upper_version moves
     DevBuf<uint8_t> d_level;
@@ -514,6 +516,62 @@ static cudaError_t launch_bf_final_metric(int cpl, const bf::BfFinalParams &fp, 
     return cudaErrorInvalidValue;
 }
 
+// K4 work plan. The tile space is n_qtiles x n_rtiles; a segment is (query tile, row-tile range,
+// result slot). Rows are cut into `s` equal splits, giving n_qtiles*s equal items in split-major order
+// (items that run at the same time cover the same rows, so X tiles are shared through L2). Whole
+// waves of P items go one item per CTA; the items left over for the last wave are each cut into f
+// finer ranges so that the last wave also keeps every CTA busy for (1/f)th of an item. s and f are
+// chosen to minimise the makespan in tiles plus a warm-up charge per segment (each segment restarts
+// its top-k threshold). Result slots per query tile: one per split, plus f-1 for a refined item.
+// Returns the number of slots; fills segs (grouped by CTA) and seg_off[ctas + 1].
+static uint32_t plan_segments(uint32_t n_qtiles, uint32_t n_rtiles, uint32_t P, uint32_t max_slots, uint32_t kp,
+                              std::vector<uint4> &segs, std::vector<uint32_t> &seg_off) {
+    const double warm = 4.0 + 0.5 * kp;                       // tiles' worth of list insertions per segment start
+    uint32_t best_s = 1, best_f = 1; double best_cost = 1e300;
+    for (uint32_t s = 1; s <= std::min<uint32_t>(n_rtiles, max_slots); ++s) {
+        const uint32_t L = (n_rtiles + s - 1) / s;
+        const uint32_t sr = (n_rtiles + L - 1) / L;           // splits that actually hold tiles
+        if (sr != s) continue;
+        const uint64_t items = static_cast<uint64_t>(n_qtiles) * sr;
+        const uint64_t full = items / P, rem = items % P;
+        uint32_t f = 0;
+        if (rem) {
+            f = static_cast<uint32_t>(std::min<uint64_t>(P / rem, std::max<uint32_t>(1, L / 8)));
+            f = std::max<uint32_t>(1, std::min<uint32_t>(f, max_slots - sr + 1));
+        }
+        const double cost = static_cast<double>(full) * L + (rem ? (L + f - 1) / f : 0) + warm * (full + (rem ? 1 : 0));
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_s = sr; best_f = std::max<uint32_t>(1, f); }
+    }
+    const uint32_t s = best_s, f = best_f;
+    const uint32_t L = (n_rtiles + s - 1) / s;
+    const uint64_t items = static_cast<uint64_t>(n_qtiles) * s;
+    const uint64_t full = items / P, rem = items % P;
+    const uint32_t ctas = static_cast<uint32_t>(std::min<uint64_t>(P, full ? P : rem * f));
+    std::vector<std::vector<uint4>> per(ctas);
+    auto item_seg = [&](uint64_t item) {
+        const uint32_t split = static_cast<uint32_t>(item / n_qtiles), qt = static_cast<uint32_t>(item % n_qtiles);
+        return make_uint4(qt, split * L, std::min<uint32_t>(n_rtiles, (split + 1) * L), split);
+    };
+    for (uint64_t w = 0; w < full; ++w)
+        for (uint32_t c = 0; c < P; ++c) per[c].push_back(item_seg(w * P + c));
+    for (uint64_t r = 0; r < rem; ++r) {
+        const uint4 it = item_seg(full * P + r);
+        const uint32_t len = it.z - it.y, sub = (len + f - 1) / f;
+        for (uint32_t j = 0; j < f; ++j) {
+            const uint32_t a = it.y + j * sub, b = std::min<uint32_t>(it.z, a + sub);
+            if (a >= b) break;
+            // sub-range j of every leftover item runs at the same time on neighbouring CTAs
+            per[(static_cast<uint64_t>(j) * rem + r) % ctas].push_back(make_uint4(it.x, a, b, j == 0 ? it.w : s + j - 1));
+        }
+    }
+    segs.clear(); seg_off.assign(1, 0u);
+    for (uint32_t c = 0; c < ctas; ++c) {
+        segs.insert(segs.end(), per[c].begin(), per[c].end());
+        seg_off.push_back(static_cast<uint32_t>(segs.size()));
+    }
+    return rem && f > 1 ? s + f - 1 : s;
+}
+
 // Device queries in, device results out, enqueued on `s`. Caller holds the lock; the device copy is current.
 static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t k, uint64_t *d_ids, float *d_dist,
                              uint32_t *d_counts, uint64_t id_stride, uint64_t id_base, cudaStream_t s) {
@@ -542,29 +600,24 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
         ix->launches++;
         ZV_CUDA(cudaGetLastError());
     }
-    // (2) work decomposition: (query tile, row split) items over one persistent CTA per SM
+    // (2) work decomposition: segments over one persistent CTA per SM (plan_segments)
     bf::BfParams p{};
     p.n = static_cast<uint32_t>(n); p.nq = static_cast<uint32_t>(nq);
     p.kchunks = pitch / bf::kBK;
     p.kp = std::min<uint32_t>(k + bf::kSlack, static_cast<uint32_t>(std::max<uint64_t>(n, 1)));
-    p.n_qtiles = static_cast<uint32_t>((nq + bf::kBM - 1) / bf::kBM);
-    p.n_rtiles = static_cast<uint32_t>((n + bf::kBN - 1) / bf::kBN);
     p.metric = g.metric;
-    const uint32_t max_splits = std::max<uint32_t>(1, std::min<uint32_t>(p.n_rtiles, std::min<uint32_t>(8192 / next_pow2(p.kp), 64)));
-    uint32_t best_s = 1; double best_eff = -1.0;
-    for (uint32_t sct = 1; sct <= max_splits; ++sct) {
-        const uint32_t tps = (p.n_rtiles + sct - 1) / sct;
-        const uint32_t real = (p.n_rtiles + tps - 1) / tps;          // splits that actually hold tiles
-        const uint64_t items = static_cast<uint64_t>(real) * p.n_qtiles;
-        const uint64_t waves = (items + ix->num_sms - 1) / ix->num_sms;
-        const double eff = static_cast<double>(items) / static_cast<double>(waves * ix->num_sms);
-        if (eff > best_eff + 0.03) { best_eff = eff; best_s = real; }
-    }
-    p.n_splits = best_s;
-    p.tiles_per_split = (p.n_rtiles + p.n_splits - 1) / p.n_splits;
-    p.n_splits = (p.n_rtiles + p.tiles_per_split - 1) / p.tiles_per_split;
-    const uint64_t items = static_cast<uint64_t>(p.n_splits) * p.n_qtiles;
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(items, ix->num_sms));
+    const uint32_t n_qtiles = static_cast<uint32_t>((nq + bf::kBM - 1) / bf::kBM);
+    const uint32_t n_rtiles = static_cast<uint32_t>((n + bf::kBN - 1) / bf::kBN);
+    const uint32_t max_slots = std::max<uint32_t>(1, std::min<uint32_t>(8192 / next_pow2(p.kp), 64));
+    std::vector<uint4> segs; std::vector<uint32_t> seg_off;
+    p.n_slots = plan_segments(n_qtiles, n_rtiles, static_cast<uint32_t>(ix->num_sms), max_slots, p.kp, segs, seg_off);
+    const unsigned grid = static_cast<unsigned>(seg_off.size() - 1);
+    ZV_CUDA(ix->bf_segs.reserve(segs.size()));
+    ZV_CUDA(ix->bf_seg_off.reserve(seg_off.size()));
+    // pageable sources: the copies are staged before cudaMemcpyAsync returns
+    ZV_CUDA(cudaMemcpyAsync(ix->bf_segs.p, segs.data(), segs.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+    ZV_CUDA(cudaMemcpyAsync(ix->bf_seg_off.p, seg_off.data(), seg_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    p.segs = ix->bf_segs.p; p.seg_off = ix->bf_seg_off.p;
     // (3) shared memory: ring stages + barriers + norms (+ the per-thread lists when they fit)
     const size_t fixed = 1024 + 16 * sizeof(uint64_t) + 2 * bf::kBN * sizeof(float) + 64;
     const size_t lists = static_cast<size_t>(p.kp) * 128 * sizeof(uint64_t);
@@ -577,8 +630,10 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
         ZV_CUDA(ix->bf_glists.reserve(static_cast<size_t>(grid) * p.kp * 128));
         p.glists = ix->bf_glists.p;
     }
-    ZV_CUDA(ix->bf_part.reserve(static_cast<size_t>(p.n_splits) * nq * p.kp));
+    ZV_CUDA(ix->bf_part.reserve(static_cast<size_t>(p.n_slots) * nq * p.kp));
     p.part_keys = ix->bf_part.p;
+    if (p.n_slots > 1)   // slots a query tile does not use must read as empty lists
+        ZV_CUDA(cudaMemsetAsync(p.part_keys, 0xFF, static_cast<size_t>(p.n_slots) * nq * p.kp * sizeof(uint64_t), s));
     p.xnorm = ix->bf_xnorm.p;
     CUtensorMap tm_qhi, tm_qlo, tm_xhi, tm_xlo;
     int rc;
@@ -586,8 +641,13 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     if ((rc = make_tile_map(&tm_qlo, ix->bf_qlo.p, nq, pitch))) return rc;
     if ((rc = make_tile_map(&tm_xhi, ix->bf_xhi.p, n, pitch))) return rc;
     if ((rc = make_tile_map(&tm_xlo, ix->bf_xlo.p, n, pitch))) return rc;
-    ZV_CUDA(cudaFuncSetAttribute(bf::bf_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    bf::bf_gemm_topk_kernel<<<grid, bf::kThreads, smem, s>>>(tm_qhi, tm_qlo, tm_xhi, tm_xlo, p);
+    if (lists_in_smem) {
+        ZV_CUDA(cudaFuncSetAttribute(bf::bf_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        bf::bf_gemm_topk_kernel<false><<<grid, bf::kThreads, smem, s>>>(tm_qhi, tm_qlo, tm_xhi, tm_xlo, p);
+    } else {
+        ZV_CUDA(cudaFuncSetAttribute(bf::bf_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        bf::bf_gemm_topk_kernel<true><<<grid, bf::kThreads, smem, s>>>(tm_qhi, tm_qlo, tm_xhi, tm_xlo, p);
+    }
     ix->launches++;
     ZV_CUDA(cudaGetLastError());
     // (4) merge the splits, exact re-rank, write k
@@ -596,8 +656,8 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     fp.queries = d_q; fp.part_keys = p.part_keys;
     fp.ids = d_ids; fp.dist = d_dist; fp.counts = d_counts;
     fp.id_stride = id_stride; fp.id_base = id_base;
-    fp.row_chunks = pitch / 4; fp.dim = g.dim; fp.nq = p.nq; fp.k = k; fp.kp = p.kp; fp.n_splits = p.n_splits;
-    fp.p2 = next_pow2(p.n_splits * p.kp); fp.kk2 = std::max<uint32_t>(2, next_pow2(k + bf::kSlack));
+    fp.row_chunks = pitch / 4; fp.dim = g.dim; fp.nq = p.nq; fp.k = k; fp.kp = p.kp; fp.n_splits = p.n_slots;
+    fp.p2 = next_pow2(p.n_slots * p.kp); fp.kk2 = std::max<uint32_t>(2, next_pow2(k + bf::kSlack));
     const uint32_t cpl_raw = (fp.row_chunks + 31) / 32;
     const int cpl = cpl_raw <= 1 ? 1 : cpl_raw <= 2 ? 2 : cpl_raw <= 4 ? 4 : cpl_raw <= 6 ? 6 : 8;
     const size_t fsmem = (static_cast<size_t>(fp.p2) + fp.kk2) * sizeof(uint64_t);
@@ -661,7 +721,7 @@ void zvdb_destroy(zvdb_index *ix) {
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
     ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_();
     ix->d_level.free_(); ix->d_upper_base.free_(); ix->d_upper_adj.free_(); ix->seeds_buf.free_();
-    ix->bf_xhi.free_(); ix->bf_xlo.free_(); ix->bf_xnorm.free_(); ix->bf_qhi.free_(); ix->bf_qlo.free_(); ix->bf_part.free_(); ix->bf_glists.free_();
+    ix->bf_xhi.free_(); ix->bf_xlo.free_(); ix->bf_xnorm.free_(); ix->bf_qhi.free_(); ix->bf_qlo.free_(); ix->bf_part.free_(); ix->bf_glists.free_(); ix->bf_segs.free_(); ix->bf_seg_off.free_();
     delete ix;
 }
 

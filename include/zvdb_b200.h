@@ -173,7 +173,9 @@ ZVDB_API int zvdb_sync_device(zvdb_index *ix);
 /* Search-kernel variant override for tuning and tests; results are identical for every value.
  * bits 0-1: 0 = automatic, 1 = narrow (8 row loads in flight per warp), 2 = wide (16 in flight);
  * bits 2-3: where the exact visited set lives: 0 = automatic, 1 = shared-memory hash table,
- *           2 = per-CTA bitmap in global memory (persistent CTAs; used for large ef * m). */
+ *           2 = per-CTA bitmap in global memory (persistent CTAs; used for large ef * m);
+ * bits 4-5: brute-force GEMM shape: 0 = automatic, 1 = one CTA per tile (tcgen05 cta_group::1,
+ *           128 x 128), 2 = CTA pairs (cta_group::2, 256 x 256). */
 ZVDB_API int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant);
 
 /* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */

@@ -28,6 +28,10 @@ def _check_against_oracle(oracle, X, Q, k, ids, dist, counts, metric=0, Xn=None)
     assert np.all(np.diff(dist[:, :kk], axis=1) >= 0)
 
 
+BF_SINGLE, BF_PAIR = 1 << 4, 2 << 4   # zvdb_set_kernel_variant bits 4-5: cta_group::1 / cta_group::2 GEMM
+
+
+@pytest.mark.parametrize("shape", [BF_SINGLE, BF_PAIR])
 @pytest.mark.parametrize("n,dim,nq,k", [
     (5000, 128, 300, 10),      # several row tiles, 3 query tiles (last one ragged)
     (1000, 3, 17, 5),          # tiny dim: one K chunk, zero padding
@@ -35,10 +39,12 @@ def _check_against_oracle(oracle, X, Q, k, ids, dist, counts, metric=0, Xn=None)
     (50, 16, 40, 100),         # k > n
     (129, 64, 1, 1),           # single query, k = 1, ragged last row tile
     (20000, 128, 1000, 10),    # more work items than one wave of splits
+    (70000, 32, 5000, 10),     # whole waves plus a refined last wave (several segments per CTA)
 ])
-def test_bruteforce_matches_oracle(zv, oracle, n, dim, nq, k):
+def test_bruteforce_matches_oracle(zv, oracle, n, dim, nq, k, shape):
     X, Q = _gauss(n, dim, 71), _gauss(nq, dim, 72)
     h = zv.HNSW(16, 200)
+    h.set_kernel_variant(shape)
     h.insert_batch(X)
     ids, dist, counts = h.bruteforce_knn(Q, k)
     _check_against_oracle(oracle, X, Q, k, ids, dist, counts)
@@ -76,6 +82,18 @@ def test_bruteforce_agrees_with_search_distances(zv):
             if int(i) in lut:
                 assert np.float32(lut[int(i)]).view(np.uint32) == np.float32(d).view(np.uint32)
                 hits += 1
+    h.deinit()
+
+
+def test_bruteforce_pair_and_single_cta_agree_bit_for_bit(zv):
+    X, Q = _gauss(30000, 96, 81), _gauss(700, 96, 82)
+    h = zv.HNSW(16, 200)
+    h.insert_batch(X)
+    h.set_kernel_variant(BF_SINGLE)
+    a = h.bruteforce_knn(Q, 25)
+    h.set_kernel_variant(BF_PAIR)
+    b = h.bruteforce_knn(Q, 25)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and np.array_equal(a[2], b[2])
     h.deinit()
 
 

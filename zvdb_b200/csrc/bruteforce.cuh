@@ -46,7 +46,6 @@ constexpr uint32_t kUmmaK = 8;                       // K of one tcgen05.mma.kin
 constexpr uint32_t kTileBytes = kBM * kBK * 4;       // 16 KiB
 constexpr uint32_t kStageBytes = 4 * kTileBytes;     // Q_hi, Q_lo, X_hi, X_lo
 constexpr uint32_t kThreads = 192;
-constexpr uint32_t kTmemCols = 2 * kBN;              // two accumulator buffers
 constexpr uint32_t kSlack = 8;                       // candidates kept beyond k for the exact re-rank
 constexpr uint32_t kMaxStages = 3;
 
@@ -118,8 +117,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
     return d;
 }
-// Instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = 128.
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kBN >> 3) << 17) | ((kBM >> 4) << 24);
+// Instruction descriptor (built in the kernel): D = f32 (1<<4), A = B = tf32 (2<<7, 2<<10), both
+// K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 
 // This thread's candidate list: kp ascending keys, 128 entries apart (the 128 epilogue threads
 // interleave). GL = false: in shared memory, addressed as such (ld/st.shared, not generic);
@@ -153,70 +152,127 @@ __device__ __noinline__ float list_insert(const CandList<GL> L, uint32_t kp, uin
     return worst == ~0ull ? __int_as_float(0x7f800000) : key_dist(worst);
 }
 
-template <bool GL>
+// ---- 2-CTA (cta_group::2) helpers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's mbarrier (bit 24 of a shared::cluster
+// address is the CTA's rank inside the pair; clearing it names the same offset in CTA 0).
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+// commit of all prior MMAs of the pair: one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+
+// PAIR = false: one CTA per SM, UMMA 128 x 128 x 8 (cta_group::1).
+// PAIR = true : the two CTAs of a cluster (the two SMs of a TPC) run ONE UMMA 256 x 256 x 8
+//   (cta_group::2): CTA r holds queries [r*128, r*128+128) of a 256-query tile and rows [r*128, ..+128)
+//   of a 256-row tile in its own shared memory, and receives the 128 x 256 accumulator of its queries
+//   in its own TMEM. Per MMA cycle each SM then reads half the shared-memory bytes of the 1-CTA shape
+//   (the 1-CTA kernel is bound by the 128 B/clk shared-memory port: 128 B/clk of operand reads plus
+//   85 B/clk of TMA writes at full tensor rate). Only the leader (rank 0) issues MMAs; both CTAs run a
+//   TMA producer (completion counted on the leader's barrier) and an epilogue; commits are multicast
+//   to both CTAs' barriers; the peer's epilogue frees accumulators by arriving on the leader's barrier.
+template <bool GL, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                     const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                     const BfParams p) {
+    constexpr uint32_t kTN = PAIR ? 2 * kBN : kBN;                  // rows per tile (UMMA N)
+    constexpr uint32_t kCols = 2 * kTN;                             // TMEM columns: two accumulator buffers
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kTN >> 3) << 17) | (((PAIR ? 2 * kBM : kBM) >> 4) << 24);
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA tiles want a 1024-byte aligned base
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + static_cast<size_t>(p.stages) * kStageBytes);
     uint64_t *full = bars, *empty = bars + kMaxStages, *tfull = bars + 2 * kMaxStages, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
-    float *xn_s = reinterpret_cast<float *>(bars + 16);                           // [2][128], 16-byte aligned (read as float4)
-    uint64_t *lists_s = reinterpret_cast<uint64_t *>(xn_s + 2 * kBN);             // [kp][128] when in smem
+    float *xn_s = reinterpret_cast<float *>(bars + 16);                           // [2][kTN], 16-byte aligned (read as float4)
+    uint64_t *lists_s = reinterpret_cast<uint64_t *>(xn_s + 2 * 2 * kBN);         // [kp][128] when in smem
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;            // CTA within the pair
+    const uint32_t unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;      // scheduling unit: CTA or CTA pair
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (uint32_t b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+        for (uint32_t b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, PAIR ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t seg_begin = __ldg(p.seg_off + blockIdx.x), seg_end = __ldg(p.seg_off + blockIdx.x + 1);
+    const uint32_t seg_begin = __ldg(p.seg_off + unit), seg_end = __ldg(p.seg_off + unit + 1);
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (both CTAs of a pair: own queries, own half of the rows) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t si = seg_begin; si < seg_end; ++si) {
                 const uint4 sg = __ldg(p.segs + si);
                 const uint32_t qt = sg.x, t0 = sg.y, t1 = sg.z;
+                const int32_t qrow = static_cast<int32_t>(PAIR ? (qt * 2 + rank) * kBM : qt * kBM);
                 for (uint32_t t = t0; t < t1; ++t) {
+                    const int32_t xrow = static_cast<int32_t>(t * kTN + rank * kBN);
                     for (uint32_t kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(empty + stage, phase ^ 1);
-                        mbar_expect_tx(full + stage, kStageBytes);
                         uint8_t *st = tiles + static_cast<size_t>(stage) * kStageBytes;
                         const int32_t kx = static_cast<int32_t>(kc * kBK);
-                        tma_load_2d(st, &tm_qhi, full + stage, kx, static_cast<int32_t>(qt * kBM));
-                        tma_load_2d(st + kTileBytes, &tm_qlo, full + stage, kx, static_cast<int32_t>(qt * kBM));
-                        tma_load_2d(st + 2 * kTileBytes, &tm_xhi, full + stage, kx, static_cast<int32_t>(t * kBN));
-                        tma_load_2d(st + 3 * kTileBytes, &tm_xlo, full + stage, kx, static_cast<int32_t>(t * kBN));
+                        if (PAIR) {
+                            if (rank == 0) mbar_expect_tx(full + stage, 2 * kStageBytes);   // both CTAs' bytes land on the leader's barrier
+                            tma_load_2d_pair(st, &tm_qhi, full + stage, kx, qrow);
+                            tma_load_2d_pair(st + kTileBytes, &tm_qlo, full + stage, kx, qrow);
+                            tma_load_2d_pair(st + 2 * kTileBytes, &tm_xhi, full + stage, kx, xrow);
+                            tma_load_2d_pair(st + 3 * kTileBytes, &tm_xlo, full + stage, kx, xrow);
+                        } else {
+                            mbar_expect_tx(full + stage, kStageBytes);
+                            tma_load_2d(st, &tm_qhi, full + stage, kx, qrow);
+                            tma_load_2d(st + kTileBytes, &tm_qlo, full + stage, kx, qrow);
+                            tma_load_2d(st + 2 * kTileBytes, &tm_xhi, full + stage, kx, xrow);
+                            tma_load_2d(st + 3 * kTileBytes, &tm_xlo, full + stage, kx, xrow);
+                        }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread =====
-        if (lane == 0) {
+        // ===== MMA issuer: one thread (of the leader CTA) =====
+        if (lane == 0 && rank == 0) {
             uint32_t stage = 0, phase = 0, tile_count = 0;
             for (uint32_t si = seg_begin; si < seg_end; ++si) {
                 const uint4 sg = __ldg(p.segs + si);
                 const uint32_t t0 = sg.y, t1 = sg.z;
                 for (uint32_t t = t0; t < t1; ++t, ++tile_count) {
                     const uint32_t buf = tile_count & 1, use = tile_count >> 1;
-                    mbar_wait(tempty + buf, (use & 1) ^ 1);          // epilogue drained this accumulator
+                    mbar_wait(tempty + buf, (use & 1) ^ 1);          // epilogue(s) drained this accumulator
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * kBN;
+                    const uint32_t d_tmem = tmem_base + buf * kTN;
                     for (uint32_t kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(full + stage, phase);
                         tc_fence_after();
@@ -226,19 +282,25 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
 #pragma unroll
                         for (uint32_t ks = 0; ks < kBK / kUmmaK; ++ks) {
                             const uint64_t off = (ks * kUmmaK * 4) >> 4;     // 32 bytes per K step, in 16-byte units
-                            tc_mma_tf32(d_tmem, q_lo + off, x_hi + off, kInstrDesc, (kc | ks) != 0);   // small terms first
-                            tc_mma_tf32(d_tmem, q_hi + off, x_lo + off, kInstrDesc, 1);
-                            tc_mma_tf32(d_tmem, q_hi + off, x_hi + off, kInstrDesc, 1);
+                            if (PAIR) {
+                                tc_mma_tf32_pair(d_tmem, q_lo + off, x_hi + off, kIdesc, (kc | ks) != 0);   // small terms first
+                                tc_mma_tf32_pair(d_tmem, q_hi + off, x_lo + off, kIdesc, 1);
+                                tc_mma_tf32_pair(d_tmem, q_hi + off, x_hi + off, kIdesc, 1);
+                            } else {
+                                tc_mma_tf32(d_tmem, q_lo + off, x_hi + off, kIdesc, (kc | ks) != 0);
+                                tc_mma_tf32(d_tmem, q_hi + off, x_lo + off, kIdesc, 1);
+                                tc_mma_tf32(d_tmem, q_hi + off, x_hi + off, kIdesc, 1);
+                            }
                         }
-                        tc_commit(empty + stage);                    // stage reusable once these MMAs retire
+                        if (PAIR) tc_commit_pair(empty + stage); else tc_commit(empty + stage);   // stage reusable once these MMAs retire
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(tfull + buf);                          // accumulator complete
+                    if (PAIR) tc_commit_pair(tfull + buf); else tc_commit(tfull + buf);           // accumulator complete
                 }
             }
         }
     } else {
-        // ===== epilogue: 4 warps, thread = one query of the tile = one TMEM lane =====
+        // ===== epilogue: 4 warps, thread = one query of the CTA's 128 = one TMEM lane =====
         const uint32_t wq = warp & 3;                                // TMEM lane quarter this warp may read
         const uint32_t et = wq * 32 + lane;                          // query row in the tile
         CandList<GL> L;
@@ -254,20 +316,21 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
             float tau = inf;
             for (uint32_t t = t0; t < t1; ++t, ++tile_count) {
                 const uint32_t buf = tile_count & 1, use = tile_count >> 1;
-                const uint32_t row0 = t * kBN;
-                {
-                    const uint32_t r = row0 + et;
-                    xn_s[buf * kBN + et] = r < p.n ? (p.metric == kMetricL2 ? __ldg(p.xnorm + r) : 0.0f) : inf;
+                const uint32_t row0 = t * kTN;
+#pragma unroll
+                for (uint32_t h = 0; h < kTN / kBN; ++h) {
+                    const uint32_t r = row0 + h * kBN + et;
+                    xn_s[buf * kTN + h * kBN + et] = r < p.n ? (p.metric == kMetricL2 ? __ldg(p.xnorm + r) : 0.0f) : inf;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");       // the 128 epilogue threads only
                 mbar_wait(tfull + buf, use & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((wq * 32u) << 16) + buf * kBN;
+                const uint32_t taddr = tmem_base + ((wq * 32u) << 16) + buf * kTN;
 #pragma unroll 1
-                for (uint32_t c = 0; c < kBN / 32; ++c) {
+                for (uint32_t c = 0; c < kTN / 32; ++c) {
                     uint32_t acc[32];
                     tc_ld32(taddr + c * 32, acc);
-                    const float4 *xn4 = reinterpret_cast<const float4 *>(xn_s + buf * kBN + c * 32);
+                    const float4 *xn4 = reinterpret_cast<const float4 *>(xn_s + buf * kTN + c * 32);
                     float d[32];
                     float mn = inf;
 #pragma unroll
@@ -289,9 +352,11 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty + buf);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_remote(tempty + buf, 0); else mbar_arrive(tempty + buf);
+                }
             }
-            const uint32_t q = qt * kBM + et;
+            const uint32_t q = (PAIR ? qt * 2 + rank : qt) * kBM + et;
             if (q < p.nq) {
                 uint64_t *out = p.part_keys + (static_cast<size_t>(slot) * p.nq + q) * p.kp;
                 for (uint32_t i = 0; i < p.kp; ++i) out[i] = L.get(i);
@@ -300,10 +365,11 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kCols) : "memory");
     }
 }
 

@@ -95,6 +95,7 @@ struct zvdb_index {
     bool descent = false;           // off = the reference's search (entry_point, layer 0 only)
     uint32_t variant = 0;           // 0 automatic, 1 narrow, 2 wide (tuning/testing)
     uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap
+    uint32_t bf_mode = 0;           // K4: 0 automatic (CTA pairs), 1 single CTAs, 2 CTA pairs
     std::atomic<uint64_t> launches{0};
 };
 
@@ -606,12 +607,16 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     p.kchunks = pitch / bf::kBK;
     p.kp = std::min<uint32_t>(k + bf::kSlack, static_cast<uint32_t>(std::max<uint64_t>(n, 1)));
     p.metric = g.metric;
-    const uint32_t n_qtiles = static_cast<uint32_t>((nq + bf::kBM - 1) / bf::kBM);
-    const uint32_t n_rtiles = static_cast<uint32_t>((n + bf::kBN - 1) / bf::kBN);
+    // CTA pairs (cta_group::2, 256 x 256 tiles) unless switched off; single CTAs (128 x 128) otherwise
+    const bool pair = ix->bf_mode != 1 && ix->num_sms >= 2;
+    const uint32_t tile_q = pair ? 2 * bf::kBM : bf::kBM, tile_r = pair ? 2 * bf::kBN : bf::kBN;
+    const uint32_t n_qtiles = static_cast<uint32_t>((nq + tile_q - 1) / tile_q);
+    const uint32_t n_rtiles = static_cast<uint32_t>((n + tile_r - 1) / tile_r);
+    const uint32_t units = pair ? static_cast<uint32_t>(ix->num_sms) / 2 : static_cast<uint32_t>(ix->num_sms);
     const uint32_t max_slots = std::max<uint32_t>(1, std::min<uint32_t>(8192 / next_pow2(p.kp), 64));
     std::vector<uint4> segs; std::vector<uint32_t> seg_off;
-    p.n_slots = plan_segments(n_qtiles, n_rtiles, static_cast<uint32_t>(ix->num_sms), max_slots, p.kp, segs, seg_off);
-    const unsigned grid = static_cast<unsigned>(seg_off.size() - 1);
+    p.n_slots = plan_segments(n_qtiles, n_rtiles, units, max_slots, p.kp, segs, seg_off);
+    const unsigned grid = static_cast<unsigned>(seg_off.size() - 1) * (pair ? 2u : 1u);
     ZV_CUDA(ix->bf_segs.reserve(segs.size()));
     ZV_CUDA(ix->bf_seg_off.reserve(seg_off.size()));
     // pageable sources: the copies are staged before cudaMemcpyAsync returns
@@ -619,7 +624,7 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     ZV_CUDA(cudaMemcpyAsync(ix->bf_seg_off.p, seg_off.data(), seg_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     p.segs = ix->bf_segs.p; p.seg_off = ix->bf_seg_off.p;
     // (3) shared memory: ring stages + barriers + norms (+ the per-thread lists when they fit)
-    const size_t fixed = 1024 + 16 * sizeof(uint64_t) + 2 * bf::kBN * sizeof(float) + 64;
+    const size_t fixed = 1024 + 16 * sizeof(uint64_t) + 4 * bf::kBN * sizeof(float) + 64;
     const size_t lists = static_cast<size_t>(p.kp) * 128 * sizeof(uint64_t);
     bool lists_in_smem = fixed + lists + 2 * bf::kStageBytes <= ix->smem_optin;
     size_t avail = ix->smem_optin - fixed - (lists_in_smem ? lists : 0);
@@ -641,12 +646,18 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     if ((rc = make_tile_map(&tm_qlo, ix->bf_qlo.p, nq, pitch))) return rc;
     if ((rc = make_tile_map(&tm_xhi, ix->bf_xhi.p, n, pitch))) return rc;
     if ((rc = make_tile_map(&tm_xlo, ix->bf_xlo.p, n, pitch))) return rc;
-    if (lists_in_smem) {
-        ZV_CUDA(cudaFuncSetAttribute(bf::bf_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        bf::bf_gemm_topk_kernel<false><<<grid, bf::kThreads, smem, s>>>(tm_qhi, tm_qlo, tm_xhi, tm_xlo, p);
-    } else {
-        ZV_CUDA(cudaFuncSetAttribute(bf::bf_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        bf::bf_gemm_topk_kernel<true><<<grid, bf::kThreads, smem, s>>>(tm_qhi, tm_qlo, tm_xhi, tm_xlo, p);
+    {
+        using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const bf::BfParams);
+        KernT kern = pair ? (lists_in_smem ? bf::bf_gemm_topk_kernel<false, true> : bf::bf_gemm_topk_kernel<true, true>)
+                          : (lists_in_smem ? bf::bf_gemm_topk_kernel<false, false> : bf::bf_gemm_topk_kernel<true, false>);
+        ZV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(bf::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        ZV_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_qhi, tm_qlo, tm_xhi, tm_xlo, p));
     }
     ix->launches++;
     ZV_CUDA(cudaGetLastError());
@@ -1004,9 +1015,10 @@ int zvdb_sync_device(zvdb_index *ix) {
 
 int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
-    const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u;
-    if (width > 2 || vis > 2 || variant > 15) return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap");
-    ix->variant = width; ix->visited_mode = vis;
+    const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u, bfm = (variant >> 4) & 3u;
+    if (width > 2 || vis > 2 || bfm > 2 || variant > 63)
+        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair");
+    ix->variant = width; ix->visited_mode = vis; ix->bf_mode = bfm;
     return ZVDB_OK;
 }
 

@@ -57,6 +57,8 @@ def parse_args():
     p.add_argument("--cpu-sample", type=int, default=2000, help="queries in the CPU-baseline sample")
     p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                    help="N>1: fused peer-store exchange inside the search kernel, or one NCCL all-gather")
+    p.add_argument("--descent", action="store_true", help="K2: walk the upper layers before the layer-0 search (extension; "
+                                                          "needs upper layers: the reference graph has them)")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return p.parse_args()
 
@@ -221,6 +223,8 @@ def run_ours(args):
         from zvdb_b200 import builder
         builder.build_quality_graph(h, Xs, args.m)
     h.sync_device()
+    if args.descent:
+        h.set_descent(True)
     if args.variant:
         h.set_kernel_variant(args.variant)
     build_s = time.time() - t0
@@ -333,12 +337,12 @@ def run_ours(args):
 
     # ---- timed region: W warm-up steps, then exactly K steps --------------------------------------
     launches[0] = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # sampled from the warm-up through the timed region to the end of the e2e loop
     for w in range(args.warmup):
         step(w % QUERY_BATCHES)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches[0] = 0
@@ -350,7 +354,6 @@ def run_ours(args):
         ends[s].record()
     barrier()
     wall = time.perf_counter() - t_wall
-    clocks = sampler.stop() if rank == 0 else None
     dev_ms = starts[0].elapsed_time(ends[-1])             # device time of the whole K-step region
     kern_ms = [starts[s].elapsed_time(ends[s]) for s in range(args.steps)]
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -396,6 +399,9 @@ def run_ours(args):
         e2e_step(s_ % QUERY_BATCHES)
     barrier()
     e_dt = torch.tensor([time.perf_counter() - t_e], dtype=torch.float64, device=dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + e2e loop (200 ms period)"
     if world > 1:
         dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
     e2e = {"value": nq * args.steps / float(e_dt.item()), "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4 * world,
@@ -421,9 +427,13 @@ def run_ours(args):
         O.build()
         adj, _ = h.export_layer(0)
         sample = min(args.cpu_sample, nq)
-        O.search_graph(X, adj, Qs[1][:256], ef, k)                       # warm the threads
+        kw = {}
+        if args.descent:
+            lv_, ub_, ua_ = h.export_upper_layers()
+            kw["upper"] = (lv_, ub_, ua_, h.max_level, h.descent_start)
+        O.search_graph(X, adj, Qs[1][:256], ef, k, **kw)                 # warm the threads
         t_c = time.perf_counter()
-        ref = O.search_graph(X, adj, Qs[0][:sample], ef, k)
+        ref = O.search_graph(X, adj, Qs[0][:sample], ef, k, **kw)
         c_dt = time.perf_counter() - t_c
         # parity spot-check of the measured configuration (checker, not the thing measured)
         step(0)
@@ -431,8 +441,14 @@ def run_ours(args):
         got = d_ids.cpu().numpy().view(np.uint64)[:sample]
         same = float((got == ref["ids"].astype(np.uint64)).mean())
         ev_same = bool(np.array_equal(d_evals.cpu().numpy().view(np.uint32)[:sample], ref["evals"]))
+        # (i) one thread, (iii) every thread behind one global lock (the reference's real
+        # behaviour, hnsw.zig:195-196) on a smaller slice of the same sample
+        small = Qs[0][:max(64, sample // 8)]
+        t1 = time.perf_counter(); O.search_graph(X, adj, small, ef, k, nthreads=1, **kw); one = len(small) / (time.perf_counter() - t1)
+        t1 = time.perf_counter(); O.search_graph(X, adj, small, ef, k, global_lock=True, **kw); lock = len(small) / (time.perf_counter() - t1)
         cpu = {"value": sample / c_dt, "unit": "queries/s", "cores": O.max_threads(), "kind": "port",
                "sample": f"first {sample} queries of batch 0, same graph/ef/k, one query per thread, no lock",
+               "one_thread_qps": one, "global_lock_qps_all_threads": lock,
                "ids_equal_frac_vs_gpu": same, "evals_equal_vs_gpu": ev_same}
 
     peak, peak_src = load_peaks()
@@ -445,7 +461,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.n}x{args.dim} fp32 L2 synthetic Gaussian, M={args.m}, {nq}-query batch, k={k}, "
-                               f"ef={ef}" + (f" ({ef_shard} pops/shard, id-sharded over {world} GPUs, exchange={args.exchange})" if world > 1 else ""),
+                               f"ef={ef}" + (", upper-layer descent on" if args.descent else "") + (f" ({ef_shard} pops/shard, id-sharded over {world} GPUs, exchange={args.exchange})" if world > 1 else ""),
                    "graph": "reference insert (hnsw.zig:73-170)" if args.graph == "reference" else "quality builder",
                    "l2_policy": f"index {args.n * args.dim * 4 / 1e6:.0f} MB > 126 MB L2; {QUERY_BATCHES} query batches rotated",
                    "recall_at_10": recalls[0] if recalls else None,

@@ -140,6 +140,15 @@ ZVDB_API int zvdb_export_upper_layers(const zvdb_index *ix, uint8_t *levels, uin
 ZVDB_API int zvdb_load_upper_layers(zvdb_index *ix, const uint8_t *levels, const uint32_t *upper_adj,
                                     uint64_t n_lists, uint64_t start);
 
+/* ---- on-disk format (the reference has no persistence) --------------------------
+ * zvdb_save writes the whole index -- vectors in the device layout, every layer, entry point, level
+ * generator state -- to one file ending in a checksum; zvdb_load replaces the contents of `ix` (which
+ * must have been created with the file's m and metric) by it, bit for bit: searches return the same
+ * results and further inserts grow the same graph. A 100M-row shard then costs one read instead of
+ * a rebuild. Errors: ZVDB_ERR_INVALID (unreadable, wrong magic/version/m/metric, truncated, checksum). */
+ZVDB_API int zvdb_save(const zvdb_index *ix, const char *path);
+ZVDB_API int zvdb_load(zvdb_index *ix, const char *path);
+
 /* ---- search ------------------------------------------------------------------------------ */
 
 /* HNSW(T).search(query, k), hnsw.zig:194-236: best-first from the entry point over layer 0,

@@ -52,7 +52,7 @@ constexpr uint32_t kMaxStages = 3;
 struct BfParams {
     const float *xnorm;      // [n] squared row norms (L2 only)
     uint64_t *part_keys;     // [n_slots][nq][kp] sorted candidate keys per (slot, query); ~0 where a slot is unused
-    uint64_t *glists;        // [gridDim.x][kp][128] per-thread lists when they do not fit in smem, else null
+    uint64_t *glists;        // [gridDim.x][128][kp] per-thread lists when they do not fit in smem, else null
     const uint4 *segs;       // segments (query tile, first row tile, end row tile, slot), grouped by CTA
     const uint32_t *seg_off; // [gridDim.x + 1] CTA b owns segs[seg_off[b] .. seg_off[b+1])
     uint32_t n, nq, kchunks, kp;
@@ -120,36 +120,54 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // Instruction descriptor (built in the kernel): D = f32 (1<<4), A = B = tf32 (2<<7, 2<<10), both
 // K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 
-// This thread's candidate list: kp ascending keys, 128 entries apart (the 128 epilogue threads
-// interleave). GL = false: in shared memory, addressed as such (ld/st.shared, not generic);
-// GL = true: in global memory (k too large for shared memory).
+// Candidate lists of the 128 epilogue threads of a CTA: thread t (= one query) owns kp ascending keys,
+// CONTIGUOUS ([128][kp]), so that a whole warp can work on one thread's list with one entry per lane
+// and no bank conflicts. GL = false: in shared memory, addressed as such (ld/st.shared, not generic);
+// GL = true: in global memory (k too large for shared memory; the lists stay L2-resident).
 template <bool GL>
-struct CandList {
-    uint64_t *g; uint32_t s;
-    __device__ __forceinline__ uint64_t get(uint32_t i) const {
-        if (GL) return g[static_cast<size_t>(i) * 128];
-        uint64_t v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(s + i * 1024u) : "memory"); return v;
+struct CandLists {
+    uint64_t *g; uint32_t s; uint32_t kp;
+    __device__ __forceinline__ uint64_t get(uint32_t t, uint32_t i) const {
+        if (GL) return g[static_cast<size_t>(t) * kp + i];
+        uint64_t v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(s + (t * kp + i) * 8u) : "memory"); return v;
     }
-    __device__ __forceinline__ void put(uint32_t i, uint64_t v) const {
-        if (GL) { g[static_cast<size_t>(i) * 128] = v; return; }
-        asm volatile("st.shared.b64 [%0], %1;" ::"r"(s + i * 1024u), "l"(v) : "memory");
+    __device__ __forceinline__ void put(uint32_t t, uint32_t i, uint64_t v) const {
+        if (GL) { g[static_cast<size_t>(t) * kp + i] = v; return; }
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(s + (t * kp + i) * 8u), "l"(v) : "memory");
     }
 };
 
-// Sorted insertion (ascending keys). Returns the new threshold distance. Kept out of line: it is the
-// rare path and must not cost the tile loop registers.
+// Sorted insertion of `key` into the list of thread `t`, done by the WHOLE WARP (one entry per lane):
+// a thread inserting on its own walks its list serially while the other 31 lanes wait, and a segment
+// start pays ~kp*ln(rows/kp) insertions per query. The caller guarantees key < the list's last entry
+// (or the list is not full yet), so the position is at most kp-1 and the last entry falls out.
+// Returns the list's new last key. All 32 lanes must call it with the same arguments.
 template <bool GL>
-__device__ __noinline__ float list_insert(const CandList<GL> L, uint32_t kp, uint64_t key) {
-    uint32_t pos = kp - 1;
-    while (pos > 0) {
-        const uint64_t prev = L.get(pos - 1);
-        if (prev <= key) break;
-        L.put(pos, prev);
-        --pos;
+__device__ __forceinline__ uint64_t coop_insert(const CandLists<GL> L, uint32_t t, uint64_t key, uint32_t lane) {
+    const uint32_t kp = L.kp;
+    uint32_t pos = 0;                                         // entries <= key (keys are unique: the id is in them)
+    for (uint32_t c0 = 0; c0 < kp; c0 += 32) {
+        const uint32_t i = c0 + lane;
+        const uint64_t e = i < kp ? L.get(t, i) : ~0ull;
+        const uint32_t cnt = __popc(__ballot_sync(kFullMask, e <= key));
+        pos += cnt;
+        if (cnt < 32) break;
     }
-    L.put(pos, key);
-    const uint64_t worst = L.get(kp - 1);
-    return worst == ~0ull ? __int_as_float(0x7f800000) : key_dist(worst);
+    const uint64_t below_last = kp >= 2 ? L.get(t, kp - 2) : 0ull;   // becomes the last entry unless the key does
+    // entries [pos, kp-2] move up by one, highest 32 first, so nothing is overwritten before it is read
+    for (uint32_t hi = kp - 1; hi > pos;) {
+        const uint32_t lo = max(pos + 1, hi >= 31 ? hi - 31 : 0u);
+        const uint32_t i = lo + lane;
+        uint64_t v = 0;
+        if (i <= hi) v = L.get(t, i - 1);
+        __syncwarp();
+        if (i <= hi) L.put(t, i, v);
+        __syncwarp();
+        hi = lo - 1;
+    }
+    if (lane == 0) L.put(t, pos, key);
+    __syncwarp();
+    return pos == kp - 1 ? key : below_last;
 }
 
 // ---- 2-CTA (cta_group::2) helpers ---------------------------------------------------------------
@@ -204,7 +222,7 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
     uint64_t *full = bars, *empty = bars + kMaxStages, *tfull = bars + 2 * kMaxStages, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
     float *xn_s = reinterpret_cast<float *>(bars + 16);                           // [2][kTN], 16-byte aligned (read as float4)
-    uint64_t *lists_s = reinterpret_cast<uint64_t *>(xn_s + 2 * 2 * kBN);         // [kp][128] when in smem
+    uint64_t *lists_s = reinterpret_cast<uint64_t *>(xn_s + 2 * 2 * kBN);         // [128][kp] when in smem
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;            // CTA within the pair
@@ -303,16 +321,18 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
         // ===== epilogue: 4 warps, thread = one query of the CTA's 128 = one TMEM lane =====
         const uint32_t wq = warp & 3;                                // TMEM lane quarter this warp may read
         const uint32_t et = wq * 32 + lane;                          // query row in the tile
-        CandList<GL> L;
-        L.g = GL ? p.glists + static_cast<size_t>(blockIdx.x) * p.kp * 128 + et : nullptr;
-        L.s = smem_u32(lists_s + et);
+        CandLists<GL> L;                                             // this warp's 32 lists
+        L.g = GL ? p.glists + (static_cast<size_t>(blockIdx.x) * 128 + wq * 32) * p.kp : nullptr;
+        L.s = smem_u32(lists_s + static_cast<size_t>(wq) * 32 * p.kp);
+        L.kp = p.kp;
         const float scale = p.metric == kMetricL2 ? -2.0f : -1.0f;
         const float inf = __int_as_float(0x7f800000);
         uint32_t tile_count = 0;
         for (uint32_t si = seg_begin; si < seg_end; ++si) {
             const uint4 sg = __ldg(p.segs + si);
             const uint32_t qt = sg.x, t0 = sg.y, t1 = sg.z, slot = sg.w;
-            for (uint32_t i = 0; i < p.kp; ++i) L.put(i, ~0ull);
+            for (uint32_t i = 0; i < p.kp; ++i) L.put(lane, i, ~0ull);
+            __syncwarp();
             float tau = inf;
             for (uint32_t t = t0; t < t1; ++t, ++tile_count) {
                 const uint32_t buf = tile_count & 1, use = tile_count >> 1;
@@ -342,11 +362,28 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
                         d[4 * j + 3] = fmaf(scale, __uint_as_float(acc[4 * j + 3]), x.w);
                         mn = fminf(mn, fminf(fminf(d[4 * j + 0], d[4 * j + 1]), fminf(d[4 * j + 2], d[4 * j + 3])));
                     }
-                    if (mn < tau) {
+                    if (__any_sync(kFullMask, mn < tau)) {                      // rare once tau is warm
+                        uint32_t pm = 0;                                         // this thread's columns that pass
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            // rows arrive in ascending id order, so on an exact tie the earlier id stays: strict <
-                            if (d[j] < tau) tau = list_insert<GL>(L, p.kp, pack_key(d[j], row0 + c * 32 + j));
+                        for (int j = 0; j < 32; ++j) pm |= d[j] < tau ? 1u << j : 0u;
+                        // Columns are taken in ascending order per thread (rows arrive in ascending id order, so on
+                        // an exact tie the earlier id stays: strict <); every round each thread offers its lowest
+                        // remaining column and the warp inserts the offers one list at a time.
+                        while (__any_sync(kFullMask, pm != 0)) {
+                            const int jj = pm ? __ffs(pm) - 1 : -1;
+                            pm &= pm - 1;
+                            float dsel = inf;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) dsel = j == jj ? d[j] : dsel;
+                            unsigned m = __ballot_sync(kFullMask, dsel < tau);       // tau may have tightened since pm was built
+                            while (m) {
+                                const uint32_t owner = __ffs(m) - 1;                 // the lane (= query) whose candidate this is
+                                m &= m - 1;
+                                const float dk = __shfl_sync(kFullMask, dsel, owner);
+                                const uint32_t col = __shfl_sync(kFullMask, jj, owner);
+                                const uint64_t last = coop_insert<GL>(L, owner, pack_key(dk, row0 + c * 32 + col), lane);
+                                if (lane == owner) tau = last == ~0ull ? inf : key_dist(last);
+                            }
                         }
                     }
                 }
@@ -359,7 +396,7 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
             const uint32_t q = (PAIR ? qt * 2 + rank : qt) * kBM + et;
             if (q < p.nq) {
                 uint64_t *out = p.part_keys + (static_cast<size_t>(slot) * p.nq + q) * p.kp;
-                for (uint32_t i = 0; i < p.kp; ++i) out[i] = L.get(i);
+                for (uint32_t i = 0; i < p.kp; ++i) out[i] = L.get(lane, i);
             }
         }
     }

@@ -880,6 +880,148 @@ int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t di
     return ZVDB_OK;
 }
 
+// ---- on-disk format (the reference has no persistence) -------------------------
+// One file = header | arena rows in the device layout (n x row_floats f32, zero padded) | layer-0
+// table (n x m u32) | node levels (n u8) | upper-layer lists in flat form (n_lists x m u32) | FNV-1a
+// 64-bit checksum of everything before it. Loading gives back the same index bit for bit, level
+// generator state included, so inserts continue exactly as they would have.
+namespace zvdb {
+struct FileHeader {
+    char magic[8];            // "ZVDBB200"
+    uint32_t version, dim, m, ef_construction, metric, row_floats, max_level, has_entry;
+    uint64_t n, entry, top_node, rng, n_lists;
+};
+static uint64_t fnv1a(uint64_t h, const void *data, size_t len) {
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < len; ++i) { h ^= p[i]; h *= 0x100000001B3ull; }
+    return h;
+}
+struct CheckedFile {
+    FILE *f = nullptr; uint64_t h = 0xCBF29CE484222325ull; bool ok = true;
+    ~CheckedFile() { if (f) fclose(f); }
+    void write(const void *d, size_t len) { if (len && fwrite(d, 1, len, f) != len) ok = false; h = fnv1a(h, d, len); }
+    void read(void *d, size_t len) { if (len && fread(d, 1, len, f) != len) ok = false; else h = fnv1a(h, d, len); }
+};
+}  // namespace zvdb
+
+int zvdb_save(const zvdb_index *cix, const char *path) {
+    if (!cix || !path) return fail(ZVDB_ERR_INVALID, "null argument");
+    zvdb_index *ix = const_cast<zvdb_index *>(cix);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const HostGraph &g = ix->g;
+    CheckedFile cf;
+    cf.f = fopen(path, "wb");
+    if (!cf.f) return fail(ZVDB_ERR_INVALID, std::string("save: cannot open ") + path);
+    FileHeader hd{};
+    std::memcpy(hd.magic, "ZVDBB200", 8);
+    hd.version = 1; hd.dim = g.dim; hd.m = g.m; hd.ef_construction = g.ef_construction; hd.metric = static_cast<uint32_t>(g.metric);
+    hd.row_floats = g.row_floats; hd.max_level = g.max_level; hd.has_entry = g.has_entry ? 1u : 0u;
+    hd.n = g.n; hd.entry = g.entry; hd.top_node = g.top_node; hd.rng = g.rng; hd.n_lists = g.upper_lists();
+    cf.write(&hd, sizeof hd);
+    for (uint64_t r = 0; r < g.n;) {
+        const uint64_t end = std::min<uint64_t>(g.n, (r / g.rows_per_chunk + 1) * g.rows_per_chunk);
+        cf.write(g.point(r), (end - r) * g.row_floats * sizeof(float));
+        r = end;
+    }
+    cf.write(g.adj0.data(), g.n * g.m * sizeof(uint32_t));
+    cf.write(g.level.data(), g.n);
+    std::vector<uint32_t> base(g.n), flat(hd.n_lists * g.m);
+    g.flatten_upper(base.data(), flat.data());
+    cf.write(flat.data(), flat.size() * sizeof(uint32_t));
+    const uint64_t sum = cf.h;
+    if (fwrite(&sum, 1, sizeof sum, cf.f) != sizeof sum) cf.ok = false;
+    if (fflush(cf.f) != 0) cf.ok = false;
+    return cf.ok ? ZVDB_OK : fail(ZVDB_ERR_INVALID, std::string("save: short write to ") + path);
+}
+
+int zvdb_load(zvdb_index *ix, const char *path) {
+    if (!ix || !path) return fail(ZVDB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    HostGraph &g = ix->g;
+    CheckedFile cf;
+    cf.f = fopen(path, "rb");
+    if (!cf.f) return fail(ZVDB_ERR_INVALID, std::string("load: cannot open ") + path);
+    FileHeader hd{};
+    cf.read(&hd, sizeof hd);
+    if (!cf.ok || std::memcmp(hd.magic, "ZVDBB200", 8) != 0 || hd.version != 1) return fail(ZVDB_ERR_INVALID, "load: not a zvdb_b200 index file (magic/version)");
+    if (hd.m != g.m) return fail(ZVDB_ERR_INVALID, "load: the file's m differs from this index's m");
+    if (hd.metric != static_cast<uint32_t>(g.metric)) return fail(ZVDB_ERR_INVALID, "load: the file's metric differs from this index's");
+    if (hd.n == 0 && hd.dim <= 1024) {                   // an empty index (its dim may not be fixed yet)
+        uint64_t stored = 0;
+        if (fread(&stored, 1, sizeof stored, cf.f) != sizeof stored || stored != cf.h) return fail(ZVDB_ERR_INVALID, "load: truncated file or checksum mismatch");
+        cudaSetDevice(ix->device);
+        g.reset_nodes();
+        g.dim = 0; g.row_floats = 0; g.rows_per_chunk = 0;
+        if (hd.dim) g.fix_dim(hd.dim);
+        g.ef_construction = hd.ef_construction; g.rng = hd.rng;
+        ix->n_dev = 0; ix->bf_rows = 0;
+        return ZVDB_OK;
+    }
+    if (hd.dim == 0 || hd.dim > 1024 || hd.row_floats != (hd.dim + 31u) / 32u * 32u || hd.n >= 0xFFFFFFFEull || hd.max_level > 31 ||
+        (hd.n && (hd.entry >= hd.n || hd.top_node >= hd.n)))
+        return fail(ZVDB_ERR_INVALID, "load: corrupt header");
+    cudaSetDevice(ix->device);
+    HostGraph fresh;
+    fresh.m = g.m; fresh.ef_construction = hd.ef_construction; fresh.metric = g.metric;
+    fresh.fix_dim(hd.dim);
+    try {
+        fresh.adj0.resize(hd.n * fresh.m); fresh.level.resize(hd.n); fresh.upper_off.assign(hd.n, ~0ull);
+    } catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "load: out of memory"); }
+    const uint64_t nchunks = (hd.n + fresh.rows_per_chunk - 1) / fresh.rows_per_chunk;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        float *pc = nullptr;
+        ZV_CUDA(cudaHostAlloc(&pc, static_cast<size_t>(fresh.rows_per_chunk) * fresh.row_floats * sizeof(float), cudaHostAllocDefault));
+        fresh.chunks.push_back(pc);
+    }
+    fresh.n = hd.n;
+    for (uint64_t r = 0; r < hd.n;) {
+        const uint64_t end = std::min<uint64_t>(hd.n, (r / fresh.rows_per_chunk + 1) * fresh.rows_per_chunk);
+        cf.read(fresh.point_mut(r), (end - r) * fresh.row_floats * sizeof(float));
+        r = end;
+    }
+    cf.read(fresh.adj0.data(), hd.n * fresh.m * sizeof(uint32_t));
+    cf.read(fresh.level.data(), hd.n);
+    uint64_t lists = 0;
+    for (uint64_t i = 0; i < hd.n && cf.ok; ++i) { if (fresh.level[i] > 31) cf.ok = false; lists += fresh.level[i]; }
+    if (!cf.ok || lists != hd.n_lists) return fail(ZVDB_ERR_INVALID, "load: truncated or corrupt file");
+    std::vector<uint32_t> flat;
+    try { flat.resize(lists * fresh.m); } catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "load: out of memory"); }
+    cf.read(flat.data(), flat.size() * sizeof(uint32_t));
+    const uint64_t sum = cf.h;
+    uint64_t stored = 0;
+    if (!cf.ok || fread(&stored, 1, sizeof stored, cf.f) != sizeof stored || stored != sum)
+        return fail(ZVDB_ERR_INVALID, "load: truncated file or checksum mismatch");
+    for (uint64_t e = 0; e < hd.n * fresh.m; ++e)
+        if (fresh.adj0[e] != kInvalidId && fresh.adj0[e] >= hd.n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "load: neighbour id out of range");
+    for (uint32_t v : flat)
+        if (v != kInvalidId && v >= hd.n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "load: neighbour id out of range");
+    uint64_t at = 0;
+    for (uint64_t i = 0; i < hd.n; ++i) {            // rebuild the per-node blocks: list lengths, then the lists
+        const uint32_t lv = fresh.level[i];
+        if (!lv) continue;
+        fresh.upper_off[i] = fresh.upper.size();
+        for (uint32_t l = 0; l < lv; ++l) {
+            const uint32_t *list = flat.data() + (at + l) * fresh.m;
+            uint32_t c = 0;
+            while (c < fresh.m && list[c] != kInvalidId) ++c;
+            fresh.upper.push_back(c);
+        }
+        fresh.upper.insert(fresh.upper.end(), flat.begin() + at * fresh.m, flat.begin() + (at + lv) * fresh.m);
+        at += lv;
+    }
+    fresh.has_entry = hd.has_entry != 0; fresh.entry = hd.entry; fresh.max_level = hd.max_level; fresh.top_node = hd.top_node;
+    fresh.rng = hd.rng;
+    // swap the new state in; the device copy is rebuilt by the next search
+    g.release();
+    g.dim = fresh.dim; g.row_floats = fresh.row_floats; g.rows_per_chunk = fresh.rows_per_chunk; g.ef_construction = fresh.ef_construction;
+    g.n = fresh.n; g.chunks.swap(fresh.chunks); g.adj0.swap(fresh.adj0); g.level.swap(fresh.level);
+    g.upper_off.swap(fresh.upper_off); g.upper.swap(fresh.upper);
+    g.has_entry = fresh.has_entry; g.entry = fresh.entry; g.max_level = fresh.max_level; g.top_node = fresh.top_node; g.rng = fresh.rng;
+    ++g.upper_version; g.rows_uploaded = 0; g.dirty.clear(); g.adj_all_dirty = true;
+    ix->n_dev = 0; ix->bf_rows = 0;
+    return ZVDB_OK;
+}
+
 int zvdb_set_descent(zvdb_index *ix, int on) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
     std::lock_guard<std::mutex> lk(ix->mu);

@@ -206,6 +206,14 @@ class HNSW:
         adj = np.ascontiguousarray(upper_adj, np.uint32).reshape(-1, self.m) if len(upper_adj) else np.zeros((0, self.m), np.uint32)
         L.check(L.lib().zvdb_load_upper_layers(self._h, lv.ctypes.data, adj.ctypes.data if adj.size else None, adj.shape[0], start))
 
+    # -- on-disk format (no reference counterpart) -------------------------------------------------
+    def save(self, path: str) -> None:
+        L.check(L.lib().zvdb_save(self._h, str(path).encode()))
+
+    def load(self, path: str) -> None:
+        """Replace this index's contents by the file's (same m and metric required)."""
+        L.check(L.lib().zvdb_load(self._h, str(path).encode()))
+
     # -- search (hnsw.zig:194) -------------------------------------------------------------------
     def search(self, query: Sequence[float], k: int) -> list:
         """`search(query, k)`: list of Node, len = min(k, reachable); empty index -> []."""

@@ -168,6 +168,13 @@ ZVDB_API int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq
                                uint32_t k, uint32_t ef, uint64_t *ids, float *dist, uint32_t *counts,
                                uint32_t *pops, uint32_t *evals);
 
+/* Page-locked host memory for query / result buffers. zvdb_search_batch accepts any host memory; with
+ * page-locked buffers the host<->device copies run asynchronously at full PCIe rate and large batches
+ * are pipelined (copy-in, kernel and copy-out of successive chunks overlap on two streams). A Zig
+ * caller wraps these two in a std.mem.Allocator. NULL on failure (zvdb_last_error). */
+ZVDB_API void *zvdb_alloc_host(size_t bytes);
+ZVDB_API void zvdb_free_host(void *p);
+
 /* Same search with DEVICE buffers, enqueued on `stream` (a cudaStream_t; NULL = the legacy
  * default stream) without synchronising. Global ids are written as id * id_stride + id_base
  * (1, 0 for a single index; G, rank for an id-sharded one). */

@@ -105,7 +105,10 @@ if which in ("c5", "both"):
             if base_ids is None: base_ids = ids[0].copy()
             assert np.array_equal(ids[0], base_ids), "result of query 0 depends on the batch size"
             hq = Qall[:nq].copy()
-            t0 = time.perf_counter(); r = h.search_batch(hq, k, ef); e2e_ms = (time.perf_counter() - t0) * 1e3
+            h.search_batch(hq, k, ef)                       # sizes the handle's device buffers for this nq (untimed)
+            e2e_ms = 1e9
+            for _ in range(3):                              # pageable numpy buffers in and out, best of 3
+                t0 = time.perf_counter(); r = h.search_batch(hq, k, ef); e2e_ms = min(e2e_ms, (time.perf_counter() - t0) * 1e3)
             print(json.dumps({"config": "C5", "graph": graph, "ef": ef, "nq": nq, "device_ms": ms, "device_qps": nq / ms * 1e3,
                               "host_call_ms": e2e_ms, "host_call_qps": nq / e2e_ms * 1e3}), flush=True)
         h.deinit()

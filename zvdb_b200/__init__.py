@@ -6,7 +6,7 @@ mirror of the reference interface used by the tests and the benchmark; it raises
 the library has not been built and never falls back to a CPU implementation.
 """
 from ._lib import METRIC_COSINE, METRIC_DOT, METRIC_L2, INVALID_ID, ZvdbError, lib  # noqa: F401
-from .hnsw import HNSW, Node, merge_topk_device  # noqa: F401
+from .hnsw import HNSW, Node, PinnedArray, merge_topk_device  # noqa: F401
 
-__all__ = ["HNSW", "Node", "ZvdbError", "lib", "merge_topk_device", "METRIC_L2", "METRIC_COSINE", "METRIC_DOT",
+__all__ = ["HNSW", "Node", "ZvdbError", "lib", "merge_topk_device", "PinnedArray", "METRIC_L2", "METRIC_COSINE", "METRIC_DOT",
            "INVALID_ID"]

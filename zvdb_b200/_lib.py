@@ -41,6 +41,8 @@ SIGNATURES = {
     "zvdb_load_upper_layers": (_i32, [_vp, _vp, _vp, _u64, _u64]),
     "zvdb_save": (_i32, [_vp, C.c_char_p]),
     "zvdb_load": (_i32, [_vp, C.c_char_p]),
+    "zvdb_alloc_host": (_vp, [C.c_size_t]),
+    "zvdb_free_host": (None, [_vp]),
     "zvdb_search": (_i32, [_vp, _pf, _u32, _u32, _pu64, _pf, _pu32]),
     "zvdb_search_batch": (_i32, [_vp, _vp, _u64, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "zvdb_search_batch_device": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp]),

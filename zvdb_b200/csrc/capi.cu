@@ -1221,7 +1221,14 @@ int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_
     // streams: the copy-in of chunk c+1 and the copy-out of chunk c-1 overlap the kernel of chunk c, and
     // consecutive kernels overlap each other's tails. (Bitmap-mode launches share per-CTA state and are
     // long compared with the copies: one chunk.)
-    const uint64_t nchunks = (nq >= 4096 && plan_visited(ix, ef) == kVisSmemHash) ? 4 : 1;
+    // Pageable buffers make every copy synchronous with the host, which turns the pipeline into pure overhead:
+    // it is used only when the caller's buffers are page-locked (zvdb_alloc_host, cudaHostAlloc, cudaHostRegister).
+    auto pinned = [](const void *ptr) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const uint64_t nchunks = (nq >= 4096 && plan_visited(ix, ef) == kVisSmemHash && pinned(queries) && pinned(ids) && pinned(dist)) ? 4 : 1;
     const uint64_t per = (nq + nchunks - 1) / nchunks;
     for (uint64_t c = 0, off = 0; off < nq; ++c, off += per) {
         const uint64_t cnt = std::min<uint64_t>(per, nq - off);
@@ -1240,6 +1247,18 @@ int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_
     if (nchunks > 1) ZV_CUDA(cudaStreamSynchronize(ix->stream2));
     return ZVDB_OK;
 }
+
+void *zvdb_alloc_host(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fail(ZVDB_ERR_OUT_OF_MEMORY, "zvdb_alloc_host: cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+
+void zvdb_free_host(void *p) { if (p) cudaFreeHost(p); }
 
 int zvdb_search(zvdb_index *ix, const float *query, uint32_t dim, uint32_t k, uint64_t *ids, float *dist, uint32_t *count) {
     if (k == 0) {   // search(query, 0): zero pops, empty slice

@@ -571,15 +571,23 @@ search_layer0_kernel(const SearchParams p) {
         if (p.pops) p.pops[q] = np;
         if (p.evals) p.evals[q] = nev + (p.seeds ? __ldg(p.seeds + q).z : 0u);
     }
-    if (VIS == kVisGlobalBitmap) {       // wipe exactly the words this query set, then order the wipe before the next query's atomics
+    if (VIS == kVisGlobalBitmap) {       // wipe exactly the words this query set
         __syncwarp();
         const uint32_t nev4 = nev & ~3u;                 // the log is 16-byte aligned: four ids per load
-        for (uint32_t i = lane * 4; i < nev4; i += 128) {
-            const uint4 w = *reinterpret_cast<const uint4 *>(vlog + i);
-            bitmap[w.x >> 5] = 0u; bitmap[w.y >> 5] = 0u; bitmap[w.z >> 5] = 0u; bitmap[w.w >> 5] = 0u;
+        // The log loads are independent of the zeroing stores, but the compiler cannot know (both are plain
+        // global pointers): fetch four chunks before the first store so their L2 trips overlap.
+        for (uint32_t i = lane * 4; i < nev4; i += 512) {
+            uint4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                w[u] = i + u * 128 < nev4 ? *reinterpret_cast<const uint4 *>(vlog + i + u * 128) : make_uint4(~0u, ~0u, ~0u, ~0u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (w[u].x != ~0u) { bitmap[w[u].x >> 5] = 0u; bitmap[w[u].y >> 5] = 0u; bitmap[w[u].z >> 5] = 0u; bitmap[w[u].w >> 5] = 0u; }
+            }
         }
         if (lane < nev - nev4) bitmap[vlog[nev4 + lane] >> 5] = 0u;
-        __threadfence();
+        // the __syncwarp below orders these stores before the next query's atomics on the same words (same warp)
     }
     __syncwarp();
     }   // persistent query loop

@@ -291,6 +291,34 @@ class HNSW:
         return int(L.lib().zvdb_kernel_launches(self._h))
 
 
+class PinnedArray:
+    """A numpy array over page-locked host memory from zvdb_alloc_host (freed by .free() or on collection).
+    Pass `.array` to search_batch-style calls: page-locked buffers are copied asynchronously and large
+    batches are pipelined."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._ptr = L.lib().zvdb_alloc_host(nbytes)
+        if not self._ptr:
+            raise L.ZvdbError(L.ERR_OOM, L.lib().zvdb_last_error().decode("utf-8", "replace"))
+        buf = (C.c_char * max(nbytes, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self) -> None:
+        if getattr(self, "_ptr", None):
+            self.array = None
+            L.lib().zvdb_free_host(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def merge_topk_device(d_dist: int, d_ids: int, d_counts: int, G: int, nq: int, k: int, out_dist: int, out_ids: int,
                       out_counts: int, stream: int = 0) -> None:
     """zvdb_merge_topk_device on raw device addresses."""

@@ -191,7 +191,11 @@ ZVDB_API int zvdb_sync_device(zvdb_index *ix);
  * bits 2-3: where the exact visited set lives: 0 = automatic, 1 = shared-memory hash table,
  *           2 = per-CTA bitmap in global memory (persistent CTAs; used for large ef * m);
  * bits 4-5: brute-force GEMM shape: 0 = automatic, 1 = one CTA per tile (tcgen05 cta_group::1,
- *           128 x 128), 2 = CTA pairs (cta_group::2, 256 x 256). */
+ *           128 x 128), 2 = CTA pairs (cta_group::2, 256 x 256). Results are identical for every value of bits 0-5.
+ * bit 6:    brute-force FILTER mode (the one setting that is NOT result-identical): the GEMM keeps only the
+ *           hi*hi TF32 product (scores good to ~2^-11 relative, a third of the tensor work), k+24 candidates
+ *           are then re-ranked exactly. Returned distances are still exact and bit-identical to the search
+ *           kernel's; a true neighbour can be missed only if the filter misplaces it by more than 24 ranks. */
 ZVDB_API int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant);
 
 /* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */

@@ -97,6 +97,26 @@ def test_bruteforce_pair_and_single_cta_agree_bit_for_bit(zv):
     h.deinit()
 
 
+def test_bruteforce_filter_mode_is_near_exact_and_returns_exact_distances(zv, oracle):
+    """Bit 6 of the variant: single-product TF32 GEMM as a filter + exact re-rank of k+24 candidates."""
+    X, Q = _gauss(60000, 128, 83), _gauss(500, 128, 84)
+    h = zv.HNSW(16, 200)
+    h.insert_batch(X)
+    exact = h.bruteforce_knn(Q, 10)
+    h.set_kernel_variant(1 << 6)
+    ids, dist, counts = h.bruteforce_knn(Q, 10)
+    recall = np.mean([len(set(ids[i].tolist()) & set(exact[0][i].tolist())) / 10 for i in range(len(Q))])
+    assert recall >= 0.999, recall
+    for qi in (0, 250, 499):                     # whatever is returned carries the exact distance
+        d = oracle.dist_many(Q[qi], X, ids[qi].astype(np.uint32), oracle.DIST_TREE)
+        assert np.array_equal(d.view(np.uint32), dist[qi].view(np.uint32))
+    assert np.all(np.diff(dist, axis=1) >= 0) and np.all(counts == 10)
+    h.set_kernel_variant(0)
+    again = h.bruteforce_knn(Q, 10)
+    assert np.array_equal(again[0], exact[0])
+    h.deinit()
+
+
 def test_bruteforce_follows_inserts_and_empty_index(zv, oracle):
     h = zv.HNSW(16, 200)
     ids, dist, counts = h.bruteforce_knn(np.zeros((3, 8), np.float32), 4)

@@ -46,7 +46,8 @@ constexpr uint32_t kUmmaK = 8;                       // K of one tcgen05.mma.kin
 constexpr uint32_t kTileBytes = kBM * kBK * 4;       // 16 KiB
 constexpr uint32_t kStageBytes = 4 * kTileBytes;     // Q_hi, Q_lo, X_hi, X_lo
 constexpr uint32_t kThreads = 192;
-constexpr uint32_t kSlack = 8;                       // candidates kept beyond k for the exact re-rank
+constexpr uint32_t kSlack = 8;                       // candidates kept beyond k for the exact re-rank (3xTF32)
+constexpr uint32_t kSlackFilter = 24;                // ... when the GEMM is the single-product TF32 filter
 constexpr uint32_t kMaxStages = 3;
 
 struct BfParams {
@@ -57,6 +58,7 @@ struct BfParams {
     const uint32_t *seg_off; // [gridDim.x + 1] CTA b owns segs[seg_off[b] .. seg_off[b+1])
     uint32_t n, nq, kchunks, kp;
     uint32_t n_slots, stages, metric;
+    uint32_t terms;          // 3 = 3xTF32 (fp32-faithful scores); 1 = hi*hi only: a FILTER, ~2^-11 relative score error
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -261,18 +263,20 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
                         mbar_wait(empty + stage, phase ^ 1);
                         uint8_t *st = tiles + static_cast<size_t>(stage) * kStageBytes;
                         const int32_t kx = static_cast<int32_t>(kc * kBK);
+                        const bool lo = p.terms == 3;                                    // the lo parts feed only the two cross terms
+                        const uint32_t bytes = lo ? kStageBytes : kStageBytes / 2;
                         if (PAIR) {
-                            if (rank == 0) mbar_expect_tx(full + stage, 2 * kStageBytes);   // both CTAs' bytes land on the leader's barrier
+                            if (rank == 0) mbar_expect_tx(full + stage, 2 * bytes);      // both CTAs' bytes land on the leader's barrier
                             tma_load_2d_pair(st, &tm_qhi, full + stage, kx, qrow);
-                            tma_load_2d_pair(st + kTileBytes, &tm_qlo, full + stage, kx, qrow);
+                            if (lo) tma_load_2d_pair(st + kTileBytes, &tm_qlo, full + stage, kx, qrow);
                             tma_load_2d_pair(st + 2 * kTileBytes, &tm_xhi, full + stage, kx, xrow);
-                            tma_load_2d_pair(st + 3 * kTileBytes, &tm_xlo, full + stage, kx, xrow);
+                            if (lo) tma_load_2d_pair(st + 3 * kTileBytes, &tm_xlo, full + stage, kx, xrow);
                         } else {
-                            mbar_expect_tx(full + stage, kStageBytes);
+                            mbar_expect_tx(full + stage, bytes);
                             tma_load_2d(st, &tm_qhi, full + stage, kx, qrow);
-                            tma_load_2d(st + kTileBytes, &tm_qlo, full + stage, kx, qrow);
+                            if (lo) tma_load_2d(st + kTileBytes, &tm_qlo, full + stage, kx, qrow);
                             tma_load_2d(st + 2 * kTileBytes, &tm_xhi, full + stage, kx, xrow);
-                            tma_load_2d(st + 3 * kTileBytes, &tm_xlo, full + stage, kx, xrow);
+                            if (lo) tma_load_2d(st + 3 * kTileBytes, &tm_xlo, full + stage, kx, xrow);
                         }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
@@ -300,14 +304,19 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
 #pragma unroll
                         for (uint32_t ks = 0; ks < kBK / kUmmaK; ++ks) {
                             const uint64_t off = (ks * kUmmaK * 4) >> 4;     // 32 bytes per K step, in 16-byte units
+                            const uint32_t first = (kc | ks) != 0;
                             if (PAIR) {
-                                tc_mma_tf32_pair(d_tmem, q_lo + off, x_hi + off, kIdesc, (kc | ks) != 0);   // small terms first
-                                tc_mma_tf32_pair(d_tmem, q_hi + off, x_lo + off, kIdesc, 1);
-                                tc_mma_tf32_pair(d_tmem, q_hi + off, x_hi + off, kIdesc, 1);
+                                if (p.terms == 3) {
+                                    tc_mma_tf32_pair(d_tmem, q_lo + off, x_hi + off, kIdesc, first);   // small terms first
+                                    tc_mma_tf32_pair(d_tmem, q_hi + off, x_lo + off, kIdesc, 1);
+                                }
+                                tc_mma_tf32_pair(d_tmem, q_hi + off, x_hi + off, kIdesc, p.terms == 3 ? 1u : first);
                             } else {
-                                tc_mma_tf32(d_tmem, q_lo + off, x_hi + off, kIdesc, (kc | ks) != 0);
-                                tc_mma_tf32(d_tmem, q_hi + off, x_lo + off, kIdesc, 1);
-                                tc_mma_tf32(d_tmem, q_hi + off, x_hi + off, kIdesc, 1);
+                                if (p.terms == 3) {
+                                    tc_mma_tf32(d_tmem, q_lo + off, x_hi + off, kIdesc, first);
+                                    tc_mma_tf32(d_tmem, q_hi + off, x_lo + off, kIdesc, 1);
+                                }
+                                tc_mma_tf32(d_tmem, q_hi + off, x_hi + off, kIdesc, p.terms == 3 ? 1u : first);
                             }
                         }
                         if (PAIR) tc_commit_pair(empty + stage); else tc_commit(empty + stage);   // stage reusable once these MMAs retire
@@ -444,7 +453,7 @@ struct BfFinalParams {
     float *dist;               // [nq][k]
     uint32_t *counts;          // [nq]
     uint64_t id_stride, id_base;
-    uint32_t row_chunks, dim, nq, k, kp, n_splits, p2, kk2;   // p2 = pow2 >= n_splits*kp ; kk2 = pow2 >= k + kSlack
+    uint32_t row_chunks, dim, nq, k, kp, n_splits, p2, kk2;   // p2 = pow2 >= n_splits*kp ; kk2 = pow2 >= kp (= k + slack)
 };
 
 template <int CPL, int METRIC>
@@ -462,7 +471,7 @@ __global__ void __launch_bounds__(32) bf_finalize_kernel(const BfFinalParams p) 
         keys[i] = key;
     }
     bitonic_sort_u64(keys, p.p2);
-    const uint32_t want = min(p.k + kSlack, total);
+    const uint32_t want = min(p.kp, total);
     Chunk2 qv[CPL];
     {
         const float *qp = p.queries + static_cast<size_t>(q) * p.dim;

@@ -96,6 +96,7 @@ struct zvdb_index {
     uint32_t variant = 0;           // 0 automatic, 1 narrow, 2 wide (tuning/testing)
     uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap
     uint32_t bf_mode = 0;           // K4: 0 automatic (CTA pairs), 1 single CTAs, 2 CTA pairs
+    bool bf_filter = false;         // K4: single-product TF32 GEMM as a candidate filter (approximate) instead of 3xTF32
     std::atomic<uint64_t> launches{0};
 };
 
@@ -605,7 +606,8 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     bf::BfParams p{};
     p.n = static_cast<uint32_t>(n); p.nq = static_cast<uint32_t>(nq);
     p.kchunks = pitch / bf::kBK;
-    p.kp = std::min<uint32_t>(k + bf::kSlack, static_cast<uint32_t>(std::max<uint64_t>(n, 1)));
+    p.terms = ix->bf_filter ? 1u : 3u;
+    p.kp = std::min<uint32_t>(k + (ix->bf_filter ? bf::kSlackFilter : bf::kSlack), static_cast<uint32_t>(std::max<uint64_t>(n, 1)));
     p.metric = g.metric;
     // CTA pairs (cta_group::2, 256 x 256 tiles) unless switched off; single CTAs (128 x 128) otherwise
     const bool pair = ix->bf_mode != 1 && ix->num_sms >= 2;
@@ -668,7 +670,7 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     fp.ids = d_ids; fp.dist = d_dist; fp.counts = d_counts;
     fp.id_stride = id_stride; fp.id_base = id_base;
     fp.row_chunks = pitch / 4; fp.dim = g.dim; fp.nq = p.nq; fp.k = k; fp.kp = p.kp; fp.n_splits = p.n_slots;
-    fp.p2 = next_pow2(p.n_slots * p.kp); fp.kk2 = std::max<uint32_t>(2, next_pow2(k + bf::kSlack));
+    fp.p2 = next_pow2(p.n_slots * p.kp); fp.kk2 = std::max<uint32_t>(2, next_pow2(p.kp));
     const uint32_t cpl_raw = (fp.row_chunks + 31) / 32;
     const int cpl = cpl_raw <= 1 ? 1 : cpl_raw <= 2 ? 2 : cpl_raw <= 4 ? 4 : cpl_raw <= 6 ? 6 : 8;
     const size_t fsmem = (static_cast<size_t>(fp.p2) + fp.kk2) * sizeof(uint64_t);
@@ -1158,9 +1160,9 @@ int zvdb_sync_device(zvdb_index *ix) {
 int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
     const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u, bfm = (variant >> 4) & 3u;
-    if (width > 2 || vis > 2 || bfm > 2 || variant > 63)
-        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair");
-    ix->variant = width; ix->visited_mode = vis; ix->bf_mode = bfm;
+    if (width > 2 || vis > 2 || bfm > 2 || variant > 127)
+        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter");
+    ix->variant = width; ix->visited_mode = vis; ix->bf_mode = bfm; ix->bf_filter = (variant >> 6) & 1u;
     return ZVDB_OK;
 }
 

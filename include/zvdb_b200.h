@@ -191,7 +191,9 @@ ZVDB_API int zvdb_sync_device(zvdb_index *ix);
  * bits 2-3: where the exact visited set lives: 0 = automatic, 1 = shared-memory hash table,
  *           2 = per-CTA bitmap in global memory (persistent CTAs; used for large ef * m);
  * bits 4-5: brute-force GEMM shape: 0 = automatic, 1 = one CTA per tile (tcgen05 cta_group::1,
- *           128 x 128), 2 = CTA pairs (cta_group::2, 256 x 256). Results are identical for every value of bits 0-5.
+ *           128 x 128), 2 = CTA pairs (cta_group::2, 256 x 256). Results are identical for every value of bits 0-5 and 7.
+ * bit 7:    brute-force top-k bookkeeping: 0 = automatic (append-and-compact lists when k allows), 1 = sorted
+ *           lists with warp-cooperative insertion (the large-k path) -- result-identical.
  * bit 6:    brute-force FILTER mode (the one setting that is NOT result-identical): the GEMM keeps only the
  *           hi*hi TF32 product (scores good to ~2^-11 relative, a third of the tensor work), k+24 candidates
  *           are then re-ranked exactly. Returned distances are still exact and bit-identical to the search

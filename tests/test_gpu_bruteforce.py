@@ -29,9 +29,10 @@ def _check_against_oracle(oracle, X, Q, k, ids, dist, counts, metric=0, Xn=None)
 
 
 BF_SINGLE, BF_PAIR = 1 << 4, 2 << 4   # zvdb_set_kernel_variant bits 4-5: cta_group::1 / cta_group::2 GEMM
+BF_SORTED = 1 << 7                    # bit 7: sorted lists + cooperative insertion instead of append-and-compact
 
 
-@pytest.mark.parametrize("shape", [BF_SINGLE, BF_PAIR])
+@pytest.mark.parametrize("shape", [BF_SINGLE, BF_PAIR, BF_PAIR | BF_SORTED])
 @pytest.mark.parametrize("n,dim,nq,k", [
     (5000, 128, 300, 10),      # several row tiles, 3 query tiles (last one ragged)
     (1000, 3, 17, 5),          # tiny dim: one K chunk, zero padding
@@ -40,6 +41,7 @@ BF_SINGLE, BF_PAIR = 1 << 4, 2 << 4   # zvdb_set_kernel_variant bits 4-5: cta_gr
     (129, 64, 1, 1),           # single query, k = 1, ragged last row tile
     (20000, 128, 1000, 10),    # more work items than one wave of splits
     (70000, 32, 5000, 10),     # whole waves plus a refined last wave (several segments per CTA)
+    (30000, 96, 700, 300),     # k + slack > 256: few result slots, several refined items per query tile
 ])
 def test_bruteforce_matches_oracle(zv, oracle, n, dim, nq, k, shape):
     X, Q = _gauss(n, dim, 71), _gauss(nq, dim, 72)
@@ -89,11 +91,13 @@ def test_bruteforce_pair_and_single_cta_agree_bit_for_bit(zv):
     X, Q = _gauss(30000, 96, 81), _gauss(700, 96, 82)
     h = zv.HNSW(16, 200)
     h.insert_batch(X)
-    h.set_kernel_variant(BF_SINGLE)
-    a = h.bruteforce_knn(Q, 25)
-    h.set_kernel_variant(BF_PAIR)
-    b = h.bruteforce_knn(Q, 25)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and np.array_equal(a[2], b[2])
+    for k in (25, 1, 60, 120, 300):             # append-and-compact with 1, 1, 4, 8 keys per lane; k = 300 -> sorted lists
+        h.set_kernel_variant(BF_SINGLE)
+        a = h.bruteforce_knn(Q, k)
+        for variant in (BF_PAIR, BF_PAIR | BF_SORTED):
+            h.set_kernel_variant(variant)
+            b = h.bruteforce_knn(Q, k)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and np.array_equal(a[2], b[2])
     h.deinit()
 
 

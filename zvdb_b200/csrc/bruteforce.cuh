@@ -53,11 +53,12 @@ constexpr uint32_t kMaxStages = 3;
 struct BfParams {
     const float *xnorm;      // [n] squared row norms (L2 only)
     uint64_t *part_keys;     // [n_slots][nq][kp] sorted candidate keys per (slot, query); ~0 where a slot is unused
-    uint64_t *glists;        // [gridDim.x][128][kp] per-thread lists when they do not fit in smem, else null
+    uint64_t *glists;        // [gridDim.x][128][cap] per-thread lists when they do not fit in smem, else null
     const uint4 *segs;       // segments (query tile, first row tile, end row tile, slot), grouped by CTA
     const uint32_t *seg_off; // [gridDim.x + 1] CTA b owns segs[seg_off[b] .. seg_off[b+1])
     uint32_t n, nq, kchunks, kp;
     uint32_t n_slots, stages, metric;
+    uint32_t cap;            // entries reserved per candidate list (= kp for EPI 0)
     uint32_t terms;          // 3 = 3xTF32 (fp32-faithful scores); 1 = hi*hi only: a FILTER, ~2^-11 relative score error
 };
 
@@ -128,16 +129,77 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // GL = true: in global memory (k too large for shared memory; the lists stay L2-resident).
 template <bool GL>
 struct CandLists {
-    uint64_t *g; uint32_t s; uint32_t kp;
+    uint64_t *g; uint32_t s; uint32_t kp; uint32_t cap;      // cap = entries reserved per thread (>= kp)
     __device__ __forceinline__ uint64_t get(uint32_t t, uint32_t i) const {
-        if (GL) return g[static_cast<size_t>(t) * kp + i];
-        uint64_t v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(s + (t * kp + i) * 8u) : "memory"); return v;
+        if (GL) return g[static_cast<size_t>(t) * cap + i];
+        uint64_t v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(s + (t * cap + i) * 8u) : "memory"); return v;
     }
     __device__ __forceinline__ void put(uint32_t t, uint32_t i, uint64_t v) const {
-        if (GL) { g[static_cast<size_t>(t) * kp + i] = v; return; }
-        asm volatile("st.shared.b64 [%0], %1;" ::"r"(s + (t * kp + i) * 8u), "l"(v) : "memory");
+        if (GL) { g[static_cast<size_t>(t) * cap + i] = v; return; }
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(s + (t * cap + i) * 8u), "l"(v) : "memory");
     }
 };
+
+// Ascending bitonic sort of 32*E keys held E per lane: key i lives in lane i % 32, register i / 32.
+template <int E>
+__device__ __forceinline__ void warp_sort_keys(uint64_t (&v)[E], uint32_t lane) {
+#pragma unroll
+    for (uint32_t k = 2; k <= 32u * E; k <<= 1) {
+#pragma unroll
+        for (uint32_t j = k >> 1; j >= 1; j >>= 1) {
+            if (j >= 32) {                                   // partner is another register of the same lane
+                const uint32_t rj = j >> 5;
+#pragma unroll
+                for (uint32_t r = 0; r < static_cast<uint32_t>(E); ++r) {
+                    if ((r & rj) == 0) {
+                        const bool asc = ((r << 5) & k) == 0;
+                        const uint64_t a = v[r], b = v[r | rj];
+                        const uint64_t lo = min(a, b), hi = max(a, b);
+                        v[r] = asc ? lo : hi; v[r | rj] = asc ? hi : lo;
+                    }
+                }
+            } else {                                         // partner is lane ^ j, same register
+#pragma unroll
+                for (uint32_t r = 0; r < static_cast<uint32_t>(E); ++r) {
+                    const uint64_t pv = shfl_xor_u64(v[r], static_cast<int>(j));
+                    const bool asc = (((r << 5) | lane) & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    v[r] = (lower == asc) ? min(v[r], pv) : max(v[r], pv);
+                }
+            }
+        }
+    }
+}
+
+// Append-and-compact top-k (the epilogue's default): a thread APPENDS a passing candidate to its own
+// unsorted list (one store, no cooperation); only when a list reaches its capacity does the warp sort
+// it in registers (32*E keys, E per lane) and keep the kp best, which also tightens that thread's
+// threshold. A compaction absorbs cap - kp appends, so the warm-up of a segment costs a few dozen
+// warp-wide sorts per query instead of ~kp*ln(rows/kp) dependent list insertions.
+// Sorts the first n_valid entries of thread t's list, leaves the kp smallest (ascending, ~0 padded) in
+// entries [0, kp), returns entry kp-1. All 32 lanes call it with the same arguments.
+template <bool GL, int E>
+__device__ __forceinline__ uint64_t compact_list(const CandLists<GL> L, uint32_t t, uint32_t n_valid, uint32_t lane) {
+    uint64_t v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const uint32_t i = r * 32u + lane;
+        v[r] = i < n_valid ? L.get(t, i) : ~0ull;
+    }
+    warp_sort_keys<E>(v, lane);
+    __syncwarp();
+    uint64_t last = ~0ull;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const uint32_t i = r * 32u + lane;
+        if (i < L.kp) L.put(t, i, v[r]);
+        const uint64_t cand = __shfl_sync(kFullMask, static_cast<uint32_t>(v[r] >> 32), (L.kp - 1) & 31);
+        const uint64_t cand_lo = __shfl_sync(kFullMask, static_cast<uint32_t>(v[r]), (L.kp - 1) & 31);
+        if (static_cast<uint32_t>(r) == ((L.kp - 1) >> 5)) last = (cand << 32) | cand_lo;
+    }
+    __syncwarp();
+    return last;
+}
 
 // Sorted insertion of `key` into the list of thread `t`, done by the WHOLE WARP (one entry per lane):
 // a thread inserting on its own walks its list serially while the other 31 lanes wait, and a segment
@@ -209,7 +271,9 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank)
 //   85 B/clk of TMA writes at full tensor rate). Only the leader (rank 0) issues MMAs; both CTAs run a
 //   TMA producer (completion counted on the leader's barrier) and an epilogue; commits are multicast
 //   to both CTAs' barriers; the peer's epilogue frees accumulators by arriving on the leader's barrier.
-template <bool GL, bool PAIR>
+// EPI: 0 = sorted lists with warp-cooperative insertion (any k); E > 0 = append-and-compact with lists of
+// up to 32*E entries per thread (kp < cap <= 32*E).
+template <bool GL, bool PAIR, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo,
                     const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
@@ -224,7 +288,7 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
     uint64_t *full = bars, *empty = bars + kMaxStages, *tfull = bars + 2 * kMaxStages, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
     float *xn_s = reinterpret_cast<float *>(bars + 16);                           // [2][kTN], 16-byte aligned (read as float4)
-    uint64_t *lists_s = reinterpret_cast<uint64_t *>(xn_s + 2 * 2 * kBN);         // [128][kp] when in smem
+    uint64_t *lists_s = reinterpret_cast<uint64_t *>(xn_s + 2 * 2 * kBN);         // [128][cap] when in smem
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;            // CTA within the pair
@@ -331,18 +395,19 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
         const uint32_t wq = warp & 3;                                // TMEM lane quarter this warp may read
         const uint32_t et = wq * 32 + lane;                          // query row in the tile
         CandLists<GL> L;                                             // this warp's 32 lists
-        L.g = GL ? p.glists + (static_cast<size_t>(blockIdx.x) * 128 + wq * 32) * p.kp : nullptr;
-        L.s = smem_u32(lists_s + static_cast<size_t>(wq) * 32 * p.kp);
-        L.kp = p.kp;
+        L.g = GL ? p.glists + (static_cast<size_t>(blockIdx.x) * 128 + wq * 32) * p.cap : nullptr;
+        L.s = smem_u32(lists_s + static_cast<size_t>(wq) * 32 * p.cap);
+        L.kp = p.kp; L.cap = p.cap;
         const float scale = p.metric == kMetricL2 ? -2.0f : -1.0f;
         const float inf = __int_as_float(0x7f800000);
         uint32_t tile_count = 0;
         for (uint32_t si = seg_begin; si < seg_end; ++si) {
             const uint4 sg = __ldg(p.segs + si);
             const uint32_t qt = sg.x, t0 = sg.y, t1 = sg.z, slot = sg.w;
-            for (uint32_t i = 0; i < p.kp; ++i) L.put(lane, i, ~0ull);
+            if (EPI == 0) { for (uint32_t i = 0; i < p.kp; ++i) L.put(lane, i, ~0ull); }
             __syncwarp();
             float tau = inf;
+            uint32_t cnt = 0;                                        // EPI > 0: entries in this thread's list
             for (uint32_t t = t0; t < t1; ++t, ++tile_count) {
                 const uint32_t buf = tile_count & 1, use = tile_count >> 1;
                 const uint32_t row0 = t * kTN;
@@ -384,14 +449,26 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
                             float dsel = inf;
 #pragma unroll
                             for (int j = 0; j < 32; ++j) dsel = j == jj ? d[j] : dsel;
-                            unsigned m = __ballot_sync(kFullMask, dsel < tau);       // tau may have tightened since pm was built
-                            while (m) {
-                                const uint32_t owner = __ffs(m) - 1;                 // the lane (= query) whose candidate this is
-                                m &= m - 1;
-                                const float dk = __shfl_sync(kFullMask, dsel, owner);
-                                const uint32_t col = __shfl_sync(kFullMask, jj, owner);
-                                const uint64_t last = coop_insert<GL>(L, owner, pack_key(dk, row0 + c * 32 + col), lane);
-                                if (lane == owner) tau = last == ~0ull ? inf : key_dist(last);
+                            if constexpr (EPI == 0) {
+                                unsigned m = __ballot_sync(kFullMask, dsel < tau);   // tau may have tightened since pm was built
+                                while (m) {
+                                    const uint32_t owner = __ffs(m) - 1;             // the lane (= query) whose candidate this is
+                                    m &= m - 1;
+                                    const float dk = __shfl_sync(kFullMask, dsel, owner);
+                                    const uint32_t col = __shfl_sync(kFullMask, jj, owner);
+                                    const uint64_t last = coop_insert<GL>(L, owner, pack_key(dk, row0 + c * 32 + col), lane);
+                                    if (lane == owner) tau = last == ~0ull ? inf : key_dist(last);
+                                }
+                            } else {
+                                if (dsel < tau) { L.put(lane, cnt, pack_key(dsel, row0 + c * 32 + jj)); ++cnt; }
+                                unsigned full = __ballot_sync(kFullMask, cnt == p.cap);
+                                while (full) {                                       // rare: once per cap - kp appends of a thread
+                                    const uint32_t owner = __ffs(full) - 1;
+                                    full &= full - 1;
+                                    __syncwarp();
+                                    const uint64_t last = compact_list<GL, EPI>(L, owner, p.cap, lane);
+                                    if (lane == owner) { cnt = p.kp; tau = key_dist(last); }
+                                }
                             }
                         }
                     }
@@ -401,6 +478,11 @@ bf_gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_qhi, const __grid_con
                 if (lane == 0) {
                     if (PAIR) mbar_arrive_remote(tempty + buf, 0); else mbar_arrive(tempty + buf);
                 }
+            }
+            if constexpr (EPI > 0) {                                 // leave every list sorted, kp long, ~0 padded
+                __syncwarp();
+                for (uint32_t owner = 0; owner < 32; ++owner)
+                    compact_list<GL, EPI>(L, owner, __shfl_sync(kFullMask, cnt, owner), lane);
             }
             const uint32_t q = (PAIR ? qt * 2 + rank : qt) * kBM + et;
             if (q < p.nq) {

@@ -96,6 +96,7 @@ struct zvdb_index {
     uint32_t variant = 0;           // 0 automatic, 1 narrow, 2 wide (tuning/testing)
     uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap
     uint32_t bf_mode = 0;           // K4: 0 automatic (CTA pairs), 1 single CTAs, 2 CTA pairs
+    uint32_t bf_epilogue = 0;       // K4: 0 automatic (append-and-compact when it applies), 1 sorted lists + cooperative insertion
     bool bf_filter = false;         // K4: single-product TF32 GEMM as a candidate filter (approximate) instead of 3xTF32
     std::atomic<uint64_t> launches{0};
 };
@@ -524,7 +525,7 @@ static cudaError_t launch_bf_final_metric(int cpl, const bf::BfFinalParams &fp, 
 // waves of P items go one item per CTA; the items left over for the last wave are each cut into f
 // finer ranges so that the last wave also keeps every CTA busy for (1/f)th of an item. s and f are
 // chosen to minimise the makespan in tiles plus a warm-up charge per segment (each segment restarts
-// its top-k threshold). Result slots per query tile: one per split, plus f-1 for a refined item.
+// its top-k threshold). Result slots per query tile: one per split, plus f-1 for each refined item of that tile.
 // Returns the number of slots; fills segs (grouped by CTA) and seg_off[ctas + 1].
 static uint32_t plan_segments(uint32_t n_qtiles, uint32_t n_rtiles, uint32_t P, uint32_t max_slots, uint32_t kp,
                               std::vector<uint4> &segs, std::vector<uint32_t> &seg_off) {
@@ -538,8 +539,10 @@ static uint32_t plan_segments(uint32_t n_qtiles, uint32_t n_rtiles, uint32_t P, 
         const uint64_t full = items / P, rem = items % P;
         uint32_t f = 0;
         if (rem) {
+            // a query tile can own several leftover items (one per split); each refined item needs f-1 extra slots
+            const uint32_t per_qt = static_cast<uint32_t>((rem + n_qtiles - 1) / n_qtiles);
             f = static_cast<uint32_t>(std::min<uint64_t>(P / rem, std::max<uint32_t>(1, L / 8)));
-            f = std::max<uint32_t>(1, std::min<uint32_t>(f, max_slots - sr + 1));
+            f = std::max<uint32_t>(1, std::min<uint32_t>(f, (max_slots - sr) / per_qt + 1));
         }
         const double cost = static_cast<double>(full) * L + (rem ? (L + f - 1) / f : 0) + warm * (full + (rem ? 1 : 0));
         if (cost < best_cost - 1e-9) { best_cost = cost; best_s = sr; best_f = std::max<uint32_t>(1, f); }
@@ -550,6 +553,8 @@ static uint32_t plan_segments(uint32_t n_qtiles, uint32_t n_rtiles, uint32_t P, 
     const uint64_t full = items / P, rem = items % P;
     const uint32_t ctas = static_cast<uint32_t>(std::min<uint64_t>(P, full ? P : rem * f));
     std::vector<std::vector<uint4>> per(ctas);
+    std::vector<uint32_t> next_slot(n_qtiles, s);             // slots 0..s-1 belong to the splits; refinements take the next free ones
+    uint32_t n_slots = s;
     auto item_seg = [&](uint64_t item) {
         const uint32_t split = static_cast<uint32_t>(item / n_qtiles), qt = static_cast<uint32_t>(item % n_qtiles);
         return make_uint4(qt, split * L, std::min<uint32_t>(n_rtiles, (split + 1) * L), split);
@@ -563,7 +568,9 @@ static uint32_t plan_segments(uint32_t n_qtiles, uint32_t n_rtiles, uint32_t P, 
             const uint32_t a = it.y + j * sub, b = std::min<uint32_t>(it.z, a + sub);
             if (a >= b) break;
             // sub-range j of every leftover item runs at the same time on neighbouring CTAs
-            per[(static_cast<uint64_t>(j) * rem + r) % ctas].push_back(make_uint4(it.x, a, b, j == 0 ? it.w : s + j - 1));
+            const uint32_t slot = j == 0 ? it.w : next_slot[it.x]++;
+            n_slots = std::max(n_slots, slot + 1);
+            per[(static_cast<uint64_t>(j) * rem + r) % ctas].push_back(make_uint4(it.x, a, b, slot));
         }
     }
     segs.clear(); seg_off.assign(1, 0u);
@@ -571,7 +578,7 @@ static uint32_t plan_segments(uint32_t n_qtiles, uint32_t n_rtiles, uint32_t P, 
         segs.insert(segs.end(), per[c].begin(), per[c].end());
         seg_off.push_back(static_cast<uint32_t>(segs.size()));
     }
-    return rem && f > 1 ? s + f - 1 : s;
+    return n_slots;
 }
 
 // Device queries in, device results out, enqueued on `s`. Caller holds the lock; the device copy is current.
@@ -627,14 +634,30 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     p.segs = ix->bf_segs.p; p.seg_off = ix->bf_seg_off.p;
     // (3) shared memory: ring stages + barriers + norms (+ the per-thread lists when they fit)
     const size_t fixed = 1024 + 16 * sizeof(uint64_t) + 4 * bf::kBN * sizeof(float) + 64;
-    const size_t lists = static_cast<size_t>(p.kp) * 128 * sizeof(uint64_t);
-    bool lists_in_smem = fixed + lists + 2 * bf::kStageBytes <= ix->smem_optin;
+    // candidate lists: append-and-compact (cap > kp entries per thread, sorted 32*E at a time) when cap fits
+    // 256 entries, in shared memory when that leaves a 3-stage ring; sorted lists with cooperative insertion else
+    const size_t room = ix->smem_optin - fixed - bf::kMaxStages * bf::kStageBytes;     // bytes left beside a full ring
+    const uint32_t room_entries = static_cast<uint32_t>(room / (128 * sizeof(uint64_t)));
+    int epi = 0;
+    bool lists_in_smem = false;
+    p.cap = p.kp;
+    if (pair && ix->bf_epilogue != 1) {
+        if (p.kp + 4 <= std::min<uint32_t>(room_entries, 32)) {      // on chip: as many spare entries as fit (<= 32 in all)
+            p.cap = std::min<uint32_t>(std::min<uint32_t>(room_entries, 32), 2 * p.kp);
+            epi = 1; lists_in_smem = true;
+        } else if (2 * p.kp <= 256) {                                // in global memory (L2): twice kp
+            p.cap = 2 * p.kp;
+            epi = p.cap <= 32 ? 1 : p.cap <= 64 ? 2 : p.cap <= 128 ? 4 : 8;
+        }
+    }
+    const size_t lists = static_cast<size_t>(p.cap) * 128 * sizeof(uint64_t);
+    if (epi == 0) lists_in_smem = fixed + lists + 2 * bf::kStageBytes <= ix->smem_optin;
     size_t avail = ix->smem_optin - fixed - (lists_in_smem ? lists : 0);
     p.stages = static_cast<uint32_t>(std::min<size_t>(bf::kMaxStages, avail / bf::kStageBytes));
     if (p.stages < 2) return fail(ZVDB_ERR_UNSUPPORTED, "bruteforce: not enough shared memory for a 2-stage ring");
     const size_t smem = fixed + p.stages * bf::kStageBytes + (lists_in_smem ? lists : 0);
     if (!lists_in_smem) {
-        ZV_CUDA(ix->bf_glists.reserve(static_cast<size_t>(grid) * p.kp * 128));
+        ZV_CUDA(ix->bf_glists.reserve(static_cast<size_t>(grid) * p.cap * 128));
         p.glists = ix->bf_glists.p;
     }
     ZV_CUDA(ix->bf_part.reserve(static_cast<size_t>(p.n_slots) * nq * p.kp));
@@ -650,8 +673,12 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     if ((rc = make_tile_map(&tm_xlo, ix->bf_xlo.p, n, pitch))) return rc;
     {
         using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const bf::BfParams);
-        KernT kern = pair ? (lists_in_smem ? bf::bf_gemm_topk_kernel<false, true> : bf::bf_gemm_topk_kernel<true, true>)
-                          : (lists_in_smem ? bf::bf_gemm_topk_kernel<false, false> : bf::bf_gemm_topk_kernel<true, false>);
+        KernT kern = nullptr;
+        if (!pair) kern = lists_in_smem ? bf::bf_gemm_topk_kernel<false, false, 0> : bf::bf_gemm_topk_kernel<true, false, 0>;
+        else if (epi == 0) kern = lists_in_smem ? bf::bf_gemm_topk_kernel<false, true, 0> : bf::bf_gemm_topk_kernel<true, true, 0>;
+        else if (lists_in_smem) kern = bf::bf_gemm_topk_kernel<false, true, 1>;
+        else kern = epi == 1 ? bf::bf_gemm_topk_kernel<true, true, 1> : epi == 2 ? bf::bf_gemm_topk_kernel<true, true, 2>
+                  : epi == 4 ? bf::bf_gemm_topk_kernel<true, true, 4> : bf::bf_gemm_topk_kernel<true, true, 8>;
         ZV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(bf::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -1160,9 +1187,9 @@ int zvdb_sync_device(zvdb_index *ix) {
 int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
     const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u, bfm = (variant >> 4) & 3u;
-    if (width > 2 || vis > 2 || bfm > 2 || variant > 127)
-        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter");
-    ix->variant = width; ix->visited_mode = vis; ix->bf_mode = bfm; ix->bf_filter = (variant >> 6) & 1u;
+    if (width > 2 || vis > 2 || bfm > 2 || variant > 255)
+        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue");
+    ix->variant = width; ix->visited_mode = vis; ix->bf_mode = bfm; ix->bf_filter = (variant >> 6) & 1u; ix->bf_epilogue = (variant >> 7) & 1u;
     return ZVDB_OK;
 }
 

@@ -59,6 +59,8 @@ def parse_args():
                    help="N>1: fused peer-store exchange inside the search kernel, or one NCCL all-gather")
     p.add_argument("--descent", action="store_true", help="K2: walk the upper layers before the layer-0 search (extension; "
                                                           "needs upper layers: the reference graph has them)")
+    p.add_argument("--shard-gen", action="store_true", help="generate each rank's rows on that rank only (large --n, e.g. C4); "
+                                                            "implies --no-cpu")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return p.parse_args()
 
@@ -68,6 +70,24 @@ def make_data(n, dim, nq, seed_x=1, seed_q=2):
     X = np.random.default_rng(seed_x).standard_normal((n, dim), dtype=np.float32)
     Qs = [np.random.default_rng(seed_q + b).standard_normal((nq, dim), dtype=np.float32) for b in range(QUERY_BATCHES)]
     return X, Qs
+
+
+def make_shard(n, dim, rank, world, seed_x=1, block=65536):
+    """Rows rank, rank+world, ... of an n-row synthetic matrix whose row blocks have their own seeds, so a
+    rank generates its shard without ever holding the whole matrix (C4: 100M x 128 does not fit a host)."""
+    out = np.empty((len(range(rank, n, world)), dim), np.float32)
+    at = 0
+    for b0 in range(0, n, block):
+        rows = min(block, n - b0)
+        first = (rank - b0) % world                       # first row of this block that belongs to the shard
+        if first >= rows:
+            continue
+        blk = np.random.default_rng([seed_x, b0 // block]).standard_normal((rows, dim), dtype=np.float32)
+        take = blk[first::world]
+        out[at:at + len(take)] = take
+        at += len(take)
+    assert at == len(out)
+    return out
 
 
 def load_peaks():
@@ -212,9 +232,14 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream().cuda_stream
 
-    X, Qs = make_data(args.n, args.dim, args.nq)
-    # id-sharding: rank r owns global ids r, r+G, r+2G, ...; one index per shard
-    Xs = X[rank::world] if world > 1 else X
+    if args.shard_gen:      # big indexes: every rank generates only its own rows (block-seeded, not make_data's matrix)
+        X = None
+        Qs = [np.random.default_rng(2 + b).standard_normal((args.nq, args.dim), dtype=np.float32) for b in range(QUERY_BATCHES)]
+        Xs = make_shard(args.n, args.dim, rank, world)
+    else:
+        X, Qs = make_data(args.n, args.dim, args.nq)
+        # id-sharding: rank r owns global ids r, r+G, r+2G, ...; one index per shard
+        Xs = X[rank::world] if world > 1 else X
     t0 = time.time()
     h = zvdb_b200.HNSW(args.m, 200, device=local)
     if args.graph == "reference":
@@ -422,7 +447,7 @@ def run_ours(args):
 
     # ---- CPU baseline: the oracle on the host cores, bounded sample of the same workload ---------
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not args.shard_gen:
         from oracle import oracle as O
         O.build()
         adj, _ = h.export_layer(0)

@@ -24,6 +24,11 @@ extern fn zvdb_get_point(ix: *const zvdb_index, id: u64) ?[*]const f32;
 extern fn zvdb_get_connections(ix: *const zvdb_index, id: u64, layer: u32, out: ?[*]u64, cap: u32, len: *u32) c_int;
 extern fn zvdb_search(ix: *zvdb_index, query: [*]const f32, dim: u32, k: u32, ids: [*]u64, dist: [*]f32, count: *u32) c_int;
 extern fn zvdb_search_batch(ix: *zvdb_index, queries: [*]const f32, nq: u64, dim: u32, k: u32, ef: u32, ids: [*]u64, dist: [*]f32, counts: [*]u32, pops: ?[*]u32, evals: ?[*]u32) c_int;
+extern fn zvdb_set_descent(ix: *zvdb_index, on: c_int) c_int;
+extern fn zvdb_save(ix: *const zvdb_index, path: [*:0]const u8) c_int;
+extern fn zvdb_load(ix: *zvdb_index, path: [*:0]const u8) c_int;
+extern fn zvdb_alloc_host(bytes: usize) ?*anyopaque;
+extern fn zvdb_free_host(p: ?*anyopaque) void;
 extern fn zvdb_last_error() [*:0]const u8;
 
 pub const Error = error{ OutOfMemory, NodeNotFound, DimMismatch, CudaError, Invalid, Unsupported };
@@ -109,6 +114,32 @@ pub fn HNSW(comptime T: type) type {
             const h = self.handle orelse return error.CudaError;
             const dim = queries.len / nq;
             try check(zvdb_search_batch(h, queries.ptr, nq, @intCast(dim), @intCast(k), @intCast(ef), ids.ptr, dist.ptr, counts.ptr, null, null));
+        }
+
+        /// Extension: walk layers max_level..1 greedily (the walk of insert, hnsw.zig:89-104) before the
+        /// layer-0 search. Off = the reference's search, which never leaves layer 0 (hnsw.zig:216).
+        pub fn setDescent(self: *Self, on: bool) !void {
+            const h = self.handle orelse return error.CudaError;
+            try check(zvdb_set_descent(h, @intFromBool(on)));
+        }
+
+        /// Extension: the whole index to / from one file (the reference has no persistence).
+        pub fn save(self: *Self, path: [:0]const u8) !void {
+            const h = self.handle orelse return error.CudaError;
+            try check(zvdb_save(h, path.ptr));
+        }
+        pub fn load(self: *Self, path: [:0]const u8) !void {
+            const h = self.handle orelse return error.CudaError;
+            try check(zvdb_load(h, path.ptr));
+        }
+
+        /// Page-locked buffers for searchBatch (asynchronous copies, pipelined large batches).
+        pub fn allocPinned(comptime E: type, n: usize) ![]E {
+            const p = zvdb_alloc_host(n * @sizeOf(E)) orelse return error.OutOfMemory;
+            return @as([*]E, @ptrCast(@alignCast(p)))[0..n];
+        }
+        pub fn freePinned(comptime E: type, buf: []E) void {
+            zvdb_free_host(@ptrCast(buf.ptr));
         }
     };
 }

@@ -45,7 +45,7 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--n", type=int, default=1_000_000)
+    p.add_argument("--n", "--rows", type=int, default=1_000_000, dest="n")   # --rows: torchrun's own parser chokes on "--n"
     p.add_argument("--dim", type=int, default=128)
     p.add_argument("--nq", type=int, default=10_000)
     p.add_argument("--k", type=int, default=10)
@@ -72,21 +72,16 @@ def make_data(n, dim, nq, seed_x=1, seed_q=2):
     return X, Qs
 
 
-def make_shard(n, dim, rank, world, seed_x=1, block=65536):
-    """Rows rank, rank+world, ... of an n-row synthetic matrix whose row blocks have their own seeds, so a
-    rank generates its shard without ever holding the whole matrix (C4: 100M x 128 does not fit a host)."""
-    out = np.empty((len(range(rank, n, world)), dim), np.float32)
-    at = 0
-    for b0 in range(0, n, block):
-        rows = min(block, n - b0)
-        first = (rank - b0) % world                       # first row of this block that belongs to the shard
-        if first >= rows:
-            continue
-        blk = np.random.default_rng([seed_x, b0 // block]).standard_normal((rows, dim), dtype=np.float32)
-        take = blk[first::world]
-        out[at:at + len(take)] = take
-        at += len(take)
-    assert at == len(out)
+def make_shard(n, dim, rank, world, seed_x=1, block=1 << 20):
+    """This rank's rows (global ids rank, rank+world, ...) of an n-row synthetic index, generated on the rank
+    that owns them from a (seed, world, rank) stream: the whole matrix never exists anywhere (C4: 100M x 128).
+    The rows are N(0,1) like make_data's, but not the same numbers; runs at different world sizes are
+    statistically, not bitwise, the same index."""
+    rows = len(range(rank, n, world))
+    out = np.empty((rows, dim), np.float32)
+    rng = np.random.default_rng([seed_x, world, rank])
+    for b0 in range(0, rows, block):
+        out[b0:b0 + block] = rng.standard_normal((min(block, rows - b0), dim), dtype=np.float32)
     return out
 
 
@@ -345,6 +340,22 @@ def run_ours(args):
             gt = exact_ground_truth(0)
             recalls.append(recall_at_k(res, gt))
     sweep = None
+    if args.sweep and world > 1:
+        # id-sharded: every rank takes part in every step; rank 0's device time of 3 lock-stepped steps is reported
+        sweep = []
+        for e in (32, 64, 128, 256, 512):
+            es = max(k, -(-e // world))
+            for _ in range(2):
+                step(0, es)
+            barrier()
+            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                step(0, es)
+            bb.record(); barrier()
+            ms = a.elapsed_time(bb) / 3
+            sweep.append({"ef": e, "pops_per_shard": es, "qps": nq / (ms * 1e-3),
+                          "recall_at_10": recall_at_k(m_ids.cpu().numpy().view(np.uint64), gt)})
     if args.sweep and rank == 0 and world == 1:
         sweep = []
         for e in (32, 64, 128, 256, 512):

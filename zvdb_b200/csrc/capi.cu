@@ -74,6 +74,8 @@ struct zvdb_index {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;  // owned; used by the host-buffer entry points and uploads
     cudaStream_t stream2 = nullptr; // owned; second lane of the chunk pipeline in zvdb_search_batch
+    cudaStream_t stream_in = nullptr; // owned; carries the pipeline's host-to-device copies, so chunk c+2 arrives while chunk c still runs
+    cudaEvent_t in_ev[8] = {};      // chunk c of the query batch is on the device
     cudaEvent_t bitmap_ev = nullptr; // last kernel that used the shared visited bitmaps
     float *d_arena = nullptr;       // [cap_rows][row_floats]
     uint32_t *d_adj = nullptr;      // [cap_rows][m]
@@ -745,6 +747,8 @@ int zvdb_create(zvdb_index **out, uint32_t dim, uint32_t m, uint32_t ef_construc
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream_in, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ix->in_ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->bitmap_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete ix; ZV_CUDA(e); }
     *out = ix;
@@ -756,6 +760,8 @@ void zvdb_destroy(zvdb_index *ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) { cudaStreamSynchronize(ix->stream); cudaStreamDestroy(ix->stream); }
     if (ix->stream2) { cudaStreamSynchronize(ix->stream2); cudaStreamDestroy(ix->stream2); }
+    if (ix->stream_in) { cudaStreamSynchronize(ix->stream_in); cudaStreamDestroy(ix->stream_in); }
+    for (int i = 0; i < 8; ++i) if (ix->in_ev[i]) cudaEventDestroy(ix->in_ev[i]);
     if (ix->bitmap_ev) cudaEventDestroy(ix->bitmap_ev);
     cudaFree(ix->d_arena); cudaFree(ix->d_adj);
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
@@ -1246,9 +1252,10 @@ int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_
     ZV_CUDA(ix->cnt_buf.reserve(nq));
     if (pops) ZV_CUDA(ix->pops_buf.reserve(nq));
     if (evals) ZV_CUDA(ix->evals_buf.reserve(nq));
-    // Large batches whose visited sets live on chip are cut into chunks that alternate between two
-    // streams: the copy-in of chunk c+1 and the copy-out of chunk c-1 overlap the kernel of chunk c, and
-    // consecutive kernels overlap each other's tails. (Bitmap-mode launches share per-CTA state and are
+    // Large batches whose visited sets live on chip are cut into four chunks. The copies in go down their own
+    // stream back to back; kernels and copies out alternate between two other streams, each kernel waiting only
+    // for its own chunk: two kernels (2 x 2500 warps fill the GPU) run while later chunks arrive and earlier
+    // results leave. (Bitmap-mode launches share per-CTA state and are
     // long compared with the copies: one chunk.)
     // Pageable buffers make every copy synchronous with the host, which turns the pipeline into pure overhead:
     // it is used only when the caller's buffers are page-locked (zvdb_alloc_host, cudaHostAlloc, cudaHostRegister).
@@ -1259,10 +1266,18 @@ int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_
     };
     const uint64_t nchunks = (nq >= 4096 && plan_visited(ix, ef) == kVisSmemHash && pinned(queries) && pinned(ids) && pinned(dist)) ? 4 : 1;
     const uint64_t per = (nq + nchunks - 1) / nchunks;
+    if (nchunks > 1) {   // all copies in go down their own stream, back to back; kernels and copies out alternate between two others
+        for (uint64_t c = 0, off = 0; off < nq; ++c, off += per) {
+            const uint64_t cnt = std::min<uint64_t>(per, nq - off);
+            ZV_CUDA(cudaMemcpyAsync(ix->q_buf.p + off * dim, queries + off * dim, cnt * dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream_in));
+            ZV_CUDA(cudaEventRecord(ix->in_ev[c], ix->stream_in));
+        }
+    }
     for (uint64_t c = 0, off = 0; off < nq; ++c, off += per) {
         const uint64_t cnt = std::min<uint64_t>(per, nq - off);
         cudaStream_t s = (c & 1) ? ix->stream2 : ix->stream;
-        ZV_CUDA(cudaMemcpyAsync(ix->q_buf.p + off * dim, queries + off * dim, cnt * dim * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (nchunks > 1) ZV_CUDA(cudaStreamWaitEvent(s, ix->in_ev[c], 0));
+        else ZV_CUDA(cudaMemcpyAsync(ix->q_buf.p, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, s));
         rc = launch_search(ix, ix->q_buf.p + off * dim, cnt, k, ef, ix->ids_buf.p + off * k, ix->dist_buf.p + off * k, ix->cnt_buf.p + off,
                            pops ? ix->pops_buf.p + off : nullptr, evals ? ix->evals_buf.p + off : nullptr, 1, 0, s);
         if (rc) return rc;

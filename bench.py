@@ -39,6 +39,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner on
+# init), so file descriptor 1 is pointed at stderr for the whole run and the line goes to a saved copy.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -61,6 +82,8 @@ def parse_args():
                                                           "needs upper layers: the reference graph has them)")
     p.add_argument("--shard-gen", action="store_true", help="generate each rank's rows on that rank only (large --n, e.g. C4); "
                                                             "implies --no-cpu")
+    p.add_argument("--no-recall", action="store_true", help="skip the exact ground truth (K4 needs 2x the arena for its operand split: "
+                                                            "a 100M-row index on one GPU has no room for it)")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     return p.parse_args()
 
@@ -198,7 +221,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.n}x{args.dim} fp32 L2, M={args.m}, k={args.k}, ef={args.ef}, "
                                f"graph=reference-insert, {sample}-query sample of the {args.nq}-query batch per step"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
@@ -206,7 +229,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -337,8 +360,8 @@ def run_ours(args):
         evals_mean.append(float(ev.mean())); pops_mean.append(float(po.mean()))
         if b == 0:
             res = (m_ids if world > 1 else d_ids).cpu().numpy().view(np.uint64).copy()
-            gt = exact_ground_truth(0)
-            recalls.append(recall_at_k(res, gt))
+            gt = None if args.no_recall else exact_ground_truth(0)
+            recalls.append(None if gt is None else recall_at_k(res, gt))
     sweep = None
     if args.sweep and world > 1:
         # id-sharded: every rank takes part in every step; rank 0's device time of 3 lock-stepped steps is reported
@@ -355,7 +378,7 @@ def run_ours(args):
             bb.record(); barrier()
             ms = a.elapsed_time(bb) / 3
             sweep.append({"ef": e, "pops_per_shard": es, "qps": nq / (ms * 1e-3),
-                          "recall_at_10": recall_at_k(m_ids.cpu().numpy().view(np.uint64), gt)})
+                          "recall_at_10": None if gt is None else recall_at_k(m_ids.cpu().numpy().view(np.uint64), gt)})
     if args.sweep and rank == 0 and world == 1:
         sweep = []
         for e in (32, 64, 128, 256, 512):
@@ -367,7 +390,7 @@ def run_ours(args):
             ms = a.elapsed_time(bb)
             ev, po = d_evals.cpu().numpy().view(np.uint32), d_pops.cpu().numpy().view(np.uint32)
             by = algorithmic_bytes(ev, po, row_bytes, args.m, args.dim, k)
-            sweep.append({"ef": e, "qps": nq / (ms * 1e-3), "recall_at_10": recall_at_k(d_ids.cpu().numpy().view(np.uint64), gt),
+            sweep.append({"ef": e, "qps": nq / (ms * 1e-3), "recall_at_10": None if gt is None else recall_at_k(d_ids.cpu().numpy().view(np.uint64), gt),
                           "evals_per_query": float(ev.mean()), "hbm_gbs": by / (ms * 1e-3) / 1e9})
     torch.cuda.empty_cache()
 
@@ -511,7 +534,7 @@ def run_ours(args):
     }
     if sweep:
         line["sweep"] = sweep
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         backend.close()
@@ -520,6 +543,7 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

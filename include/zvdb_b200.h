@@ -80,6 +80,23 @@ ZVDB_API int zvdb_insert(zvdb_index *ix, const float *point, uint32_t dim);
 ZVDB_API int zvdb_insert_batch(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim,
                                const int32_t *levels);
 
+/* HNSW(T) for T = f64 / i32 (hnsw.zig:8 is generic; test_hnsw.zig:239-273 uses HNSW(i32) and HNSW(f64)).
+ * dtype: 0 = f32, 1 = f64, 2 = i32; like dim, the element type is fixed by the first insert and every
+ * later insert and search must use it. The caller's rows are kept as given (zvdb_get_point_typed returns
+ * them: Node.point), the graph is built comparing distances in T's own arithmetic, as the reference
+ * does, and the search runs on the f32 conversion of the rows: ids and order equal the reference's
+ * except where two distances tie within f32 rounding (~1e-7 relative), distances are returned as f32.
+ * Squared L2 only, like the reference. */
+ZVDB_API int zvdb_insert_typed(zvdb_index *ix, const void *point, uint32_t dim, int dtype);
+ZVDB_API int zvdb_insert_batch_typed(zvdb_index *ix, const void *points, uint64_t n, uint32_t dim, int dtype,
+                                     const int32_t *levels);
+ZVDB_API int zvdb_search_typed(zvdb_index *ix, const void *query, uint32_t dim, int dtype, uint32_t k, uint64_t *ids,
+                               float *dist, uint32_t *count);
+ZVDB_API int zvdb_search_batch_typed(zvdb_index *ix, const void *queries, uint64_t nq, uint32_t dim, int dtype,
+                                     uint32_t k, uint32_t ef, uint64_t *ids, float *dist, uint32_t *counts);
+ZVDB_API int zvdb_dtype(const zvdb_index *ix);
+ZVDB_API const void *zvdb_get_point_typed(const zvdb_index *ix, uint64_t id);
+
 /* hnsw.nodes.count(), the one field the reference's tests read (test_hnsw.zig:198). */
 ZVDB_API uint64_t zvdb_count(const zvdb_index *ix);
 ZVDB_API uint32_t zvdb_dim(const zvdb_index *ix);

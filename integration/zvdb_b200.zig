@@ -7,8 +7,8 @@
 //! `insert(point)`, `search(query, k) ![]const Node`, and `nodes.count()`. Every search runs in
 //! the CUDA kernels behind the `extern fn`s; there is no CPU path in this file.
 //!
-//! Only `T == f32` is accelerated (the configs of the benchmark are f32); other element types are a
-//! compile error here, so a caller who needs `HNSW(i32)` / `HNSW(f64)` keeps the CPU implementation.
+//! `T` may be f32, f64 or i32 (the reference's tests use all three, test_hnsw.zig:239-273). f64 / i32 rows are
+//! kept as given, the graph is built in T's arithmetic, the search runs on the f32 conversion of the rows.
 
 const std = @import("std");
 const Allocator = std.mem.Allocator;
@@ -24,6 +24,10 @@ extern fn zvdb_get_point(ix: *const zvdb_index, id: u64) ?[*]const f32;
 extern fn zvdb_get_connections(ix: *const zvdb_index, id: u64, layer: u32, out: ?[*]u64, cap: u32, len: *u32) c_int;
 extern fn zvdb_search(ix: *zvdb_index, query: [*]const f32, dim: u32, k: u32, ids: [*]u64, dist: [*]f32, count: *u32) c_int;
 extern fn zvdb_search_batch(ix: *zvdb_index, queries: [*]const f32, nq: u64, dim: u32, k: u32, ef: u32, ids: [*]u64, dist: [*]f32, counts: [*]u32, pops: ?[*]u32, evals: ?[*]u32) c_int;
+extern fn zvdb_insert_typed(ix: *zvdb_index, point: *const anyopaque, dim: u32, dtype: c_int) c_int;
+extern fn zvdb_search_typed(ix: *zvdb_index, query: *const anyopaque, dim: u32, dtype: c_int, k: u32, ids: [*]u64, dist: [*]f32, count: *u32) c_int;
+extern fn zvdb_search_batch_typed(ix: *zvdb_index, queries: *const anyopaque, nq: u64, dim: u32, dtype: c_int, k: u32, ef: u32, ids: [*]u64, dist: [*]f32, counts: [*]u32) c_int;
+extern fn zvdb_get_point_typed(ix: *const zvdb_index, id: u64) ?*const anyopaque;
 extern fn zvdb_set_descent(ix: *zvdb_index, on: c_int) c_int;
 extern fn zvdb_save(ix: *const zvdb_index, path: [*:0]const u8) c_int;
 extern fn zvdb_load(ix: *zvdb_index, path: [*:0]const u8) c_int;
@@ -46,7 +50,12 @@ fn check(rc: c_int) Error!void {
 }
 
 pub fn HNSW(comptime T: type) type {
-    if (T != f32) @compileError("zvdb_b200 accelerates HNSW(f32) only");
+    const dtype: c_int = switch (T) {
+        f32 => 0,
+        f64 => 1,
+        i32 => 2,
+        else => @compileError("zvdb_b200 provides HNSW(f32), HNSW(f64) and HNSW(i32)"),
+    };
     return struct {
         const Self = @This();
 
@@ -55,7 +64,7 @@ pub fn HNSW(comptime T: type) type {
         pub const Node = struct {
             id: usize,
             point: []const T,
-            distance: T, // squared L2 to the query; the reference recomputes it, we hand it back
+            distance: f32, // squared L2 to the query, computed on the device in f32; the reference recomputes it in T
         };
 
         /// Stand-in for the `nodes` hash map: tests only call `.count()` (test_hnsw.zig:198).
@@ -89,7 +98,7 @@ pub fn HNSW(comptime T: type) type {
 
         pub fn insert(self: *Self, point: []const T) !void { // hnsw.zig:73-117
             const h = self.handle orelse return error.CudaError;
-            try check(zvdb_insert(h, point.ptr, @intCast(point.len)));
+            try check(zvdb_insert_typed(h, @ptrCast(point.ptr), @intCast(point.len), dtype));
         }
 
         /// hnsw.zig:194-236: the caller owns (and frees with `allocator`) the returned slice.
@@ -100,11 +109,12 @@ pub fn HNSW(comptime T: type) type {
             const dist = try self.allocator.alloc(f32, k);
             defer self.allocator.free(dist);
             var count: u32 = 0;
-            try check(zvdb_search(h, query.ptr, @intCast(query.len), @intCast(k), ids.ptr, dist.ptr, &count));
+            try check(zvdb_search_typed(h, @ptrCast(query.ptr), @intCast(query.len), dtype, @intCast(k), ids.ptr, dist.ptr, &count));
             const out = try self.allocator.alloc(Node, count);
             const dim = zvdb_dim(h);
             for (out, 0..) |*n, i| {
-                n.* = .{ .id = @intCast(ids[i]), .point = zvdb_get_point(h, ids[i]).?[0..dim], .distance = dist[i] };
+                const row: [*]const T = @ptrCast(@alignCast(zvdb_get_point_typed(h, ids[i]).?));
+                n.* = .{ .id = @intCast(ids[i]), .point = row[0..dim], .distance = dist[i] };
             }
             return out;
         }
@@ -113,7 +123,7 @@ pub fn HNSW(comptime T: type) type {
         pub fn searchBatch(self: *Self, queries: []const T, nq: usize, k: usize, ef: usize, ids: []u64, dist: []f32, counts: []u32) !void {
             const h = self.handle orelse return error.CudaError;
             const dim = queries.len / nq;
-            try check(zvdb_search_batch(h, queries.ptr, nq, @intCast(dim), @intCast(k), @intCast(ef), ids.ptr, dist.ptr, counts.ptr, null, null));
+            try check(zvdb_search_batch_typed(h, @ptrCast(queries.ptr), nq, @intCast(dim), dtype, @intCast(k), @intCast(ef), ids.ptr, dist.ptr, counts.ptr));
         }
 
         /// Extension: walk layers max_level..1 greedily (the walk of insert, hnsw.zig:89-104) before the

@@ -25,6 +25,12 @@ SIGNATURES = {
     "zvdb_set_level_seed": (_i32, [_vp, _u64]),
     "zvdb_insert": (_i32, [_vp, _pf, _u32]),
     "zvdb_insert_batch": (_i32, [_vp, _pf, _u64, _u32, _pi32]),
+    "zvdb_insert_typed": (_i32, [_vp, _vp, _u32, _i32]),
+    "zvdb_insert_batch_typed": (_i32, [_vp, _vp, _u64, _u32, _i32, _pi32]),
+    "zvdb_search_typed": (_i32, [_vp, _vp, _u32, _i32, _u32, _pu64, _pf, _pu32]),
+    "zvdb_search_batch_typed": (_i32, [_vp, _vp, _u64, _u32, _i32, _u32, _u32, _vp, _vp, _vp]),
+    "zvdb_dtype": (_i32, [_vp]),
+    "zvdb_get_point_typed": (_vp, [_vp, _u64]),
     "zvdb_count": (_u64, [_vp]),
     "zvdb_dim": (_u32, [_vp]),
     "zvdb_max_level": (_u32, [_vp]),

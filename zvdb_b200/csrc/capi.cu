@@ -778,10 +778,22 @@ int zvdb_set_level_seed(zvdb_index *ix, uint64_t seed) {
     return ZVDB_OK;
 }
 
-static int insert_locked(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, const int32_t *levels) {
+// f64 / i32 -> the f32 the device works on (round to nearest; i32 is exact below 2^24)
+static void to_f32(const void *src, uint64_t count, int dtype, float *dst) {
+    if (dtype == 1) { const double *p = static_cast<const double *>(src); for (uint64_t i = 0; i < count; ++i) dst[i] = static_cast<float>(p[i]); }
+    else if (dtype == 2) { const int32_t *p = static_cast<const int32_t *>(src); for (uint64_t i = 0; i < count; ++i) dst[i] = static_cast<float>(p[i]); }
+    else std::memcpy(dst, src, count * sizeof(float));
+}
+
+static int insert_locked(zvdb_index *ix, const void *points_any, uint64_t n, uint32_t dim, const int32_t *levels, int dtype = 0) {
     HostGraph &g = ix->g;
     if (n == 0) return ZVDB_OK;
-    if (!points) return fail(ZVDB_ERR_INVALID, "insert: null point");
+    if (!points_any) return fail(ZVDB_ERR_INVALID, "insert: null point");
+    if (dtype < 0 || dtype > 2) return fail(ZVDB_ERR_INVALID, "insert: dtype must be 0 (f32), 1 (f64) or 2 (i32)");
+    if (g.n == 0 && g.chunks.empty()) g.dtype = dtype;   // HNSW(T): the element type is fixed by the first insert, like dim
+    if (dtype != g.dtype) return fail(ZVDB_ERR_INVALID, "insert: element type differs from the index's (one HNSW(T) holds one T)");
+    if (dtype != 0 && g.metric != 0) return fail(ZVDB_ERR_UNSUPPORTED, "insert: f64 / i32 indexes are squared-L2 only, like the reference");
+    const float *points = static_cast<const float *>(points_any);
     if (g.dim == 0) {
         if (dim == 0) return fail(ZVDB_ERR_INVALID, "insert: dim must be >= 1");
         if (dim > 1024) return fail(ZVDB_ERR_UNSUPPORTED, "insert: dim > 1024 is not built into the search kernel");
@@ -789,9 +801,19 @@ static int insert_locked(zvdb_index *ix, const float *points, uint64_t n, uint32
     }
     if (dim != g.dim) return fail(ZVDB_ERR_DIM_MISMATCH, "Mismatched dimensions in distance calculation");
     cudaSetDevice(ix->device);
+    if (dtype == 0) {
+        for (uint64_t i = 0; i < n; ++i) {
+            if (g.insert(points + i * static_cast<uint64_t>(dim), levels ? levels[i] : -1))
+                return fail(ZVDB_ERR_OUT_OF_MEMORY, "insert: out of memory");
+        }
+        return ZVDB_OK;
+    }
+    std::vector<float> conv(dim);
+    const size_t es = g.elem_size();
     for (uint64_t i = 0; i < n; ++i) {
-        if (g.insert(points + i * static_cast<uint64_t>(dim), levels ? levels[i] : -1))
-            return fail(ZVDB_ERR_OUT_OF_MEMORY, "insert: out of memory");
+        const unsigned char *src = static_cast<const unsigned char *>(points_any) + i * static_cast<uint64_t>(dim) * es;
+        to_f32(src, dim, dtype, conv.data());
+        if (g.insert(conv.data(), levels ? levels[i] : -1, src)) return fail(ZVDB_ERR_OUT_OF_MEMORY, "insert: out of memory");
     }
     return ZVDB_OK;
 }
@@ -806,6 +828,46 @@ int zvdb_insert_batch(zvdb_index *ix, const float *points, uint64_t n, uint32_t 
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
     std::lock_guard<std::mutex> lk(ix->mu);
     return insert_locked(ix, points, n, dim, levels);
+}
+
+int zvdb_insert_typed(zvdb_index *ix, const void *point, uint32_t dim, int dtype) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return insert_locked(ix, point, 1, dim, nullptr, dtype);
+}
+
+int zvdb_insert_batch_typed(zvdb_index *ix, const void *points, uint64_t n, uint32_t dim, int dtype, const int32_t *levels) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return insert_locked(ix, points, n, dim, levels, dtype);
+}
+
+int zvdb_dtype(const zvdb_index *ix) { return ix ? ix->g.dtype : 0; }
+
+const void *zvdb_get_point_typed(const zvdb_index *ix, uint64_t id) {
+    if (!ix || id >= ix->g.n) return nullptr;
+    return ix->g.typed_point(id);
+}
+
+int zvdb_search_batch_typed(zvdb_index *ix, const void *queries, uint64_t nq, uint32_t dim, int dtype, uint32_t k, uint32_t ef,
+                            uint64_t *ids, float *dist, uint32_t *counts) {
+    if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
+    if (dtype < 0 || dtype > 2) return fail(ZVDB_ERR_INVALID, "search: dtype must be 0 (f32), 1 (f64) or 2 (i32)");
+    if (dtype == 0) return zvdb_search_batch(ix, static_cast<const float *>(queries), nq, dim, k, ef, ids, dist, counts, nullptr, nullptr);
+    if (nq && !queries) return fail(ZVDB_ERR_INVALID, "search: null buffer");
+    if (ix->g.n && dtype != ix->g.dtype) return fail(ZVDB_ERR_INVALID, "search: element type differs from the index's");
+    std::vector<float> conv;
+    try { conv.resize(nq * static_cast<uint64_t>(dim)); } catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "search: out of memory"); }
+    to_f32(queries, conv.size(), dtype, conv.data());
+    return zvdb_search_batch(ix, conv.data(), nq, dim, k, ef, ids, dist, counts, nullptr, nullptr);
+}
+
+int zvdb_search_typed(zvdb_index *ix, const void *query, uint32_t dim, int dtype, uint32_t k, uint64_t *ids, float *dist, uint32_t *count) {
+    if (k == 0) {
+        if (count) *count = 0;
+        return ix ? ZVDB_OK : fail(ZVDB_ERR_INVALID, "null index");
+    }
+    return zvdb_search_batch_typed(ix, query, 1, dim, dtype, k, k, ids, dist, count);
 }
 
 uint64_t zvdb_count(const zvdb_index *ix) { return ix ? ix->g.n : 0; }
@@ -863,6 +925,7 @@ static int set_points_locked(zvdb_index *ix, const float *points, uint64_t n, ui
     if (n && entry >= n) return fail(ZVDB_ERR_NODE_NOT_FOUND, "entry out of range");
     cudaSetDevice(ix->device);
     g.reset_nodes();
+    g.dtype = 0;                    // loaded / built graphs are f32
     g.fix_dim(dim);
     try {
         g.adj0.assign(n * g.m, kInvalidId);
@@ -916,7 +979,8 @@ int zvdb_load_graph(zvdb_index *ix, const float *points, uint64_t n, uint32_t di
 }
 
 // ---- on-disk format (the reference has no persistence) -------------------------
-// One file = header | arena rows in the device layout (n x row_floats f32, zero padded) | layer-0
+// One file = header | arena rows in the device layout (n x row_floats f32, zero padded) | for f64 / i32
+// indexes the caller's rows as given (n x dim elements) | layer-0
 // table (n x m u32) | node levels (n u8) | upper-layer lists in flat form (n_lists x m u32) | FNV-1a
 // 64-bit checksum of everything before it. Loading gives back the same index bit for bit, level
 // generator state included, so inserts continue exactly as they would have.
@@ -924,6 +988,7 @@ namespace zvdb {
 struct FileHeader {
     char magic[8];            // "ZVDBB200"
     uint32_t version, dim, m, ef_construction, metric, row_floats, max_level, has_entry;
+    uint32_t dtype, reserved;   // element type of the caller's rows (0 f32, 1 f64, 2 i32); typed rows follow the arena when != 0
     uint64_t n, entry, top_node, rng, n_lists;
 };
 static uint64_t fnv1a(uint64_t h, const void *data, size_t len) {
@@ -949,7 +1014,7 @@ int zvdb_save(const zvdb_index *cix, const char *path) {
     if (!cf.f) return fail(ZVDB_ERR_INVALID, std::string("save: cannot open ") + path);
     FileHeader hd{};
     std::memcpy(hd.magic, "ZVDBB200", 8);
-    hd.version = 1; hd.dim = g.dim; hd.m = g.m; hd.ef_construction = g.ef_construction; hd.metric = static_cast<uint32_t>(g.metric);
+    hd.version = 2; hd.dtype = static_cast<uint32_t>(g.dtype); hd.dim = g.dim; hd.m = g.m; hd.ef_construction = g.ef_construction; hd.metric = static_cast<uint32_t>(g.metric);
     hd.row_floats = g.row_floats; hd.max_level = g.max_level; hd.has_entry = g.has_entry ? 1u : 0u;
     hd.n = g.n; hd.entry = g.entry; hd.top_node = g.top_node; hd.rng = g.rng; hd.n_lists = g.upper_lists();
     cf.write(&hd, sizeof hd);
@@ -957,6 +1022,13 @@ int zvdb_save(const zvdb_index *cix, const char *path) {
         const uint64_t end = std::min<uint64_t>(g.n, (r / g.rows_per_chunk + 1) * g.rows_per_chunk);
         cf.write(g.point(r), (end - r) * g.row_floats * sizeof(float));
         r = end;
+    }
+    if (g.dtype != 0) {
+        for (uint64_t r = 0; r < g.n;) {
+            const uint64_t end = std::min<uint64_t>(g.n, (r / g.rows_per_chunk + 1) * g.rows_per_chunk);
+            cf.write(g.typed_point(r), (end - r) * g.dim * g.elem_size());
+            r = end;
+        }
     }
     cf.write(g.adj0.data(), g.n * g.m * sizeof(uint32_t));
     cf.write(g.level.data(), g.n);
@@ -978,7 +1050,7 @@ int zvdb_load(zvdb_index *ix, const char *path) {
     if (!cf.f) return fail(ZVDB_ERR_INVALID, std::string("load: cannot open ") + path);
     FileHeader hd{};
     cf.read(&hd, sizeof hd);
-    if (!cf.ok || std::memcmp(hd.magic, "ZVDBB200", 8) != 0 || hd.version != 1) return fail(ZVDB_ERR_INVALID, "load: not a zvdb_b200 index file (magic/version)");
+    if (!cf.ok || std::memcmp(hd.magic, "ZVDBB200", 8) != 0 || hd.version != 2 || hd.dtype > 2) return fail(ZVDB_ERR_INVALID, "load: not a zvdb_b200 index file (magic/version)");
     if (hd.m != g.m) return fail(ZVDB_ERR_INVALID, "load: the file's m differs from this index's m");
     if (hd.metric != static_cast<uint32_t>(g.metric)) return fail(ZVDB_ERR_INVALID, "load: the file's metric differs from this index's");
     if (hd.n == 0 && hd.dim <= 1024) {                   // an empty index (its dim may not be fixed yet)
@@ -988,7 +1060,7 @@ int zvdb_load(zvdb_index *ix, const char *path) {
         g.reset_nodes();
         g.dim = 0; g.row_floats = 0; g.rows_per_chunk = 0;
         if (hd.dim) g.fix_dim(hd.dim);
-        g.ef_construction = hd.ef_construction; g.rng = hd.rng;
+        g.ef_construction = hd.ef_construction; g.rng = hd.rng; g.dtype = 0;
         ix->n_dev = 0; ix->bf_rows = 0;
         return ZVDB_OK;
     }
@@ -997,7 +1069,7 @@ int zvdb_load(zvdb_index *ix, const char *path) {
         return fail(ZVDB_ERR_INVALID, "load: corrupt header");
     cudaSetDevice(ix->device);
     HostGraph fresh;
-    fresh.m = g.m; fresh.ef_construction = hd.ef_construction; fresh.metric = g.metric;
+    fresh.m = g.m; fresh.ef_construction = hd.ef_construction; fresh.metric = g.metric; fresh.dtype = static_cast<int>(hd.dtype);
     fresh.fix_dim(hd.dim);
     try {
         fresh.adj0.resize(hd.n * fresh.m); fresh.level.resize(hd.n); fresh.upper_off.assign(hd.n, ~0ull);
@@ -1013,6 +1085,18 @@ int zvdb_load(zvdb_index *ix, const char *path) {
         const uint64_t end = std::min<uint64_t>(hd.n, (r / fresh.rows_per_chunk + 1) * fresh.rows_per_chunk);
         cf.read(fresh.point_mut(r), (end - r) * fresh.row_floats * sizeof(float));
         r = end;
+    }
+    if (fresh.dtype != 0) {
+        for (uint64_t c = 0; c < nchunks; ++c) {
+            unsigned char *tc = static_cast<unsigned char *>(std::malloc(static_cast<size_t>(fresh.rows_per_chunk) * fresh.dim * fresh.elem_size()));
+            if (!tc) return fail(ZVDB_ERR_OUT_OF_MEMORY, "load: out of memory");
+            fresh.typed_chunks.push_back(tc);
+        }
+        for (uint64_t r = 0; r < hd.n;) {
+            const uint64_t end = std::min<uint64_t>(hd.n, (r / fresh.rows_per_chunk + 1) * fresh.rows_per_chunk);
+            cf.read(const_cast<void *>(fresh.typed_point(r)), (end - r) * fresh.dim * fresh.elem_size());
+            r = end;
+        }
     }
     cf.read(fresh.adj0.data(), hd.n * fresh.m * sizeof(uint32_t));
     cf.read(fresh.level.data(), hd.n);
@@ -1049,6 +1133,7 @@ int zvdb_load(zvdb_index *ix, const char *path) {
     // swap the new state in; the device copy is rebuilt by the next search
     g.release();
     g.dim = fresh.dim; g.row_floats = fresh.row_floats; g.rows_per_chunk = fresh.rows_per_chunk; g.ef_construction = fresh.ef_construction;
+    g.dtype = fresh.dtype; g.typed_chunks.swap(fresh.typed_chunks);
     g.n = fresh.n; g.chunks.swap(fresh.chunks); g.adj0.swap(fresh.adj0); g.level.swap(fresh.level);
     g.upper_off.swap(fresh.upper_off); g.upper.swap(fresh.upper);
     g.has_entry = fresh.has_entry; g.entry = fresh.entry; g.max_level = fresh.max_level; g.top_node = fresh.top_node; g.rng = fresh.rng;

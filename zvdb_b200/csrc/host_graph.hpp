@@ -15,6 +15,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <stdexcept>
@@ -30,6 +31,11 @@ struct HostGraph {
     uint32_t row_floats = 0;        // arena row pitch in floats (multiple of 32)
     uint32_t rows_per_chunk = 0;
     std::vector<float *> chunks;    // pinned, never reallocated
+    // HNSW(T) for T = f64 / i32 (hnsw.zig:8; test_hnsw.zig:239-273): the caller's rows are kept as given (so
+    // Node.point can alias them and insert can compare distances in T's arithmetic, like the reference);
+    // the device works on the f32 conversion in `chunks`. dtype: 0 = f32 (no second copy), 1 = f64, 2 = i32.
+    int dtype = 0;
+    std::vector<unsigned char *> typed_chunks;   // rows_per_chunk rows of dim * elem_size() bytes each
     std::vector<uint32_t> adj0;     // [n][m]
     std::vector<uint8_t> level;     // node level (<= 31)
     std::vector<uint64_t> upper_off;  // offset of the node's upper-layer block in `upper`, ~0 if level 0
@@ -51,6 +57,13 @@ struct HostGraph {
     void release() {
         for (float *c : chunks) cudaFreeHost(c);
         chunks.clear();
+        for (unsigned char *c : typed_chunks) std::free(c);
+        typed_chunks.clear();
+    }
+    size_t elem_size() const { return dtype == 1 ? 8 : 4; }
+    const void *typed_point(uint64_t id) const {
+        if (dtype == 0) return point(id);
+        return typed_chunks[id / rows_per_chunk] + (id % rows_per_chunk) * static_cast<uint64_t>(dim) * elem_size();
     }
 
     void reset_nodes() {
@@ -84,6 +97,25 @@ struct HostGraph {
         }
         for (uint32_t i = 0; i < dim; ++i) { const float pr = a[i] * b[i]; sum += pr; }
         return metric == 1 ? 1.0f - sum : 0.0f - sum;
+    }
+
+    // distance between two stored nodes, as a double, in the arithmetic of the index's element type:
+    // f32 -> the f32 value above (exactly representable), f64 -> the reference's f64 sum, i32 -> the integer sum
+    // (exact in a double far beyond the i32 range in which the reference's own i32 arithmetic is defined).
+    double dist_ids(uint64_t a, uint64_t b) const {
+        if (dtype == 0) return static_cast<double>(distance(point(a), point(b)));
+        if (dtype == 1) {
+            const double *x = static_cast<const double *>(typed_point(a)), *y = static_cast<const double *>(typed_point(b));
+            double sum = 0.0;
+            if (metric == 0) { for (uint32_t i = 0; i < dim; ++i) { const double diff = x[i] - y[i]; sum += diff * diff; } return sum; }
+            for (uint32_t i = 0; i < dim; ++i) { const double pr = x[i] * y[i]; sum += pr; }
+            return metric == 1 ? 1.0 - sum : 0.0 - sum;
+        }
+        const int32_t *x = static_cast<const int32_t *>(typed_point(a)), *y = static_cast<const int32_t *>(typed_point(b));
+        int64_t sum = 0;
+        if (metric == 0) { for (uint32_t i = 0; i < dim; ++i) { const int64_t diff = static_cast<int64_t>(x[i]) - y[i]; sum += diff * diff; } return static_cast<double>(sum); }
+        for (uint32_t i = 0; i < dim; ++i) sum += static_cast<int64_t>(x[i]) * y[i];
+        return metric == 1 ? 1.0 - static_cast<double>(sum) : -static_cast<double>(sum);
     }
 
     // randomLevel, hnsw.zig:172-180: geometric p = 1/2, capped at 31 (seeded splitmix64 stands in
@@ -120,7 +152,7 @@ struct HostGraph {
     // exceed m, stable insertion sort of the m+1 ids by distance to `node` (std.sort.insertion),
     // keep the first m (the list is then distance-sorted).
     void append_and_shrink(uint64_t node, uint32_t layer, uint32_t other, std::vector<uint32_t> &tmp,
-                           std::vector<float> &tmpd) {
+                           std::vector<double> &tmpd) {
         uint32_t *list = list_ptr(node, layer);
         uint32_t len = list_len(node, layer);
         if (len < m) {
@@ -129,11 +161,10 @@ struct HostGraph {
         } else {
             tmp.assign(list, list + len);
             tmp.push_back(other);
-            const float *p = point(node);
             tmpd.resize(len + 1);
-            for (uint32_t i = 0; i <= len; ++i) tmpd[i] = distance(p, point(tmp[i]));
+            for (uint32_t i = 0; i <= len; ++i) tmpd[i] = dist_ids(node, tmp[i]);
             for (uint32_t i = 1; i <= len; ++i) {
-                const uint32_t x = tmp[i]; const float dx = tmpd[i];
+                const uint32_t x = tmp[i]; const double dx = tmpd[i];
                 uint32_t j = i;
                 while (j > 0 && dx < tmpd[j - 1]) { tmp[j] = tmp[j - 1]; tmpd[j] = tmpd[j - 1]; --j; }
                 tmp[j] = x; tmpd[j] = dx;
@@ -151,8 +182,9 @@ struct HostGraph {
         if (dirty.size() > n / 4 + 4096) { adj_all_dirty = true; dirty.clear(); dirty.shrink_to_fit(); }
     }
 
-    // insert, hnsw.zig:73-117. forced_level < 0 draws the level.
-    int insert(const float *pt, int forced_level) {
+    // insert, hnsw.zig:73-117. forced_level < 0 draws the level. `typed` (f64 / i32 indexes) is the caller's row in
+    // its own element type; `pt` its f32 conversion.
+    int insert(const float *pt, int forced_level, const void *typed = nullptr) {
         if (n >= 0xFFFFFFFEull) return 1;
         const uint64_t id = n;                                                   // :77
         const uint32_t lv = forced_level >= 0 ? static_cast<uint32_t>(forced_level > 31 ? 31 : forced_level)
@@ -162,6 +194,14 @@ struct HostGraph {
             if (cudaHostAlloc(&c, static_cast<size_t>(rows_per_chunk) * row_floats * sizeof(float),
                               cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return 1; }
             chunks.push_back(c);
+        }
+        if (dtype != 0) {
+            if (id / rows_per_chunk >= typed_chunks.size()) {
+                unsigned char *c = static_cast<unsigned char *>(std::malloc(static_cast<size_t>(rows_per_chunk) * dim * elem_size()));
+                if (!c) return 1;
+                typed_chunks.push_back(c);
+            }
+            std::memcpy(const_cast<void *>(typed_point(id)), typed, static_cast<size_t>(dim) * elem_size());
         }
         try {
             adj0.resize((id + 1) * m, kInvalidId);
@@ -190,10 +230,10 @@ struct HostGraph {
         mark_dirty(id);
 
         static thread_local std::vector<uint32_t> tmp;
-        static thread_local std::vector<float> tmpd;
+        static thread_local std::vector<double> tmpd;
         if (has_entry) {                                                         // :84
             uint64_t ep = entry;
-            float curr = distance(row, point(ep));                               // :86
+            double curr = dist_ids(id, ep);                                      // :86
             for (uint32_t layer = 0; layer <= max_level; ++layer) {              // ascending, :88
                 bool changed = true;
                 while (changed) {                                                // :90
@@ -204,7 +244,7 @@ struct HostGraph {
                         const uint32_t len = list_len(cur, layer);
                         for (uint32_t t = 0; t < len; ++t) {                     // whole captured list, :94
                             const uint32_t nb = list[t];
-                            const float d = distance(row, point(nb));
+                            const double d = dist_ids(id, nb);
                             if (d < curr) { ep = nb; curr = d; changed = true; } // strict <, :97-101
                         }
                     }

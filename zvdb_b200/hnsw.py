@@ -57,8 +57,15 @@ class _Nodes:
 class HNSW:
     """`HNSW(f32)`: init / deinit / insert / search, plus the batched entry points of the C ABI."""
 
+    _DTYPES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 2}
+
     def __init__(self, m: int = 16, ef_construction: int = 200, *, dim: int = 0, metric: int = L.METRIC_L2,
-                 device: int = 0, level_seed: Optional[int] = None):
+                 device: int = 0, level_seed: Optional[int] = None, dtype=np.float32):
+        """`dtype` is the T of `HNSW(T)`: float32 (default), float64 or int32 (test_hnsw.zig:239-273)."""
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in self._DTYPES:
+            raise TypeError("HNSW(T): T must be float32, float64 or int32")
+        self._dt = self._DTYPES[self.dtype]
         self._h = C.c_void_p()
         self.m = m
         self.ef_construction = ef_construction
@@ -105,6 +112,12 @@ class HNSW:
         return None if e < 0 else e
 
     def point(self, node_id: int) -> np.ndarray:
+        if self._dt:
+            p = L.lib().zvdb_get_point_typed(self._h, node_id)
+            if not p:
+                raise L.ZvdbError(L.ERR_NODE_NOT_FOUND, "NodeNotFound")
+            buf = (C.c_char * (self.dim * self.dtype.itemsize)).from_address(p)
+            return np.frombuffer(buf, dtype=self.dtype, count=self.dim)
         p = L.lib().zvdb_get_point(self._h, node_id)
         if not p:
             raise L.ZvdbError(L.ERR_NODE_NOT_FOUND, "NodeNotFound")
@@ -136,16 +149,24 @@ class HNSW:
 
     # -- insert (hnsw.zig:73) --------------------------------------------------------------------
     def insert(self, point: Sequence[float]) -> None:
+        if self._dt:
+            p = np.ascontiguousarray(point, self.dtype).reshape(-1)
+            L.check(L.lib().zvdb_insert_typed(self._h, p.ctypes.data, p.size, self._dt))
+            return
         p = np.ascontiguousarray(point, np.float32).reshape(-1)
         L.check(L.lib().zvdb_insert(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.size))
 
     def insert_batch(self, points, levels=None) -> None:
-        p = np.ascontiguousarray(points, np.float32)
+        p = np.ascontiguousarray(points, self.dtype)
         if p.ndim != 2:
             raise ValueError("points must be [n, dim]")
         lv = None
         if levels is not None:
             lv = np.ascontiguousarray(levels, np.int32)
+        if self._dt:
+            L.check(L.lib().zvdb_insert_batch_typed(self._h, p.ctypes.data, p.shape[0], p.shape[1], self._dt,
+                                                    lv.ctypes.data_as(C.POINTER(C.c_int32)) if lv is not None else None))
+            return
         L.check(L.lib().zvdb_insert_batch(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.shape[0], p.shape[1],
                                           lv.ctypes.data_as(C.POINTER(C.c_int32)) if lv is not None else None))
 
@@ -217,28 +238,39 @@ class HNSW:
     # -- search (hnsw.zig:194) -------------------------------------------------------------------
     def search(self, query: Sequence[float], k: int) -> list:
         """`search(query, k)`: list of Node, len = min(k, reachable); empty index -> []."""
-        q = np.ascontiguousarray(query, np.float32).reshape(-1)
+        q = np.ascontiguousarray(query, self.dtype).reshape(-1)
         if k == 0:
             return []
         ids = np.empty(k, np.uint64)
         dist = np.empty(k, np.float32)
         cnt = C.c_uint32(0)
-        L.check(L.lib().zvdb_search(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, k,
-                                    ids.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                    dist.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt)))
+        if self._dt:
+            L.check(L.lib().zvdb_search_typed(self._h, q.ctypes.data, q.size, self._dt, k,
+                                              ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              dist.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt)))
+        else:
+            L.check(L.lib().zvdb_search(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, k,
+                                        ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        dist.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cnt)))
         return [Node(int(ids[i]), self.point(int(ids[i])), float(dist[i]), self) for i in range(cnt.value)]
 
     def search_batch(self, queries, k: int, ef: int = 0, counters: bool = False):
         """Rows q: search(queries[q], ef)[0..k]. Host arrays in, host arrays out (copies are inside).
 
         Returns (ids[nq,k] u64, dist[nq,k] f32, counts[nq] u32[, pops[nq], evals[nq]])."""
-        q = np.ascontiguousarray(queries, np.float32)
+        q = np.ascontiguousarray(queries, self.dtype)
         if q.ndim == 1:
             q = q.reshape(1, -1)
         nq, dim = q.shape
         ids = np.empty((nq, k), np.uint64)
         dist = np.empty((nq, k), np.float32)
         counts = np.empty(nq, np.uint32)
+        if self._dt:
+            if counters:
+                raise ValueError("counters are reported for float32 indexes only")
+            L.check(L.lib().zvdb_search_batch_typed(self._h, q.ctypes.data, nq, dim, self._dt, k, ef, ids.ctypes.data,
+                                                    dist.ctypes.data, counts.ctypes.data))
+            return ids, dist, counts
         pops = np.empty(nq, np.uint32) if counters else None
         evals = np.empty(nq, np.uint32) if counters else None
         L.check(L.lib().zvdb_search_batch(self._h, q.ctypes.data, nq, dim, k, ef, ids.ctypes.data, dist.ctypes.data,

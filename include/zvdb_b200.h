@@ -214,7 +214,10 @@ ZVDB_API int zvdb_sync_device(zvdb_index *ix);
  * bit 6:    brute-force FILTER mode (the one setting that is NOT result-identical): the GEMM keeps only the
  *           hi*hi TF32 product (scores good to ~2^-11 relative, a third of the tensor work), k+24 candidates
  *           are then re-ranked exactly. Returned distances are still exact and bit-identical to the search
- *           kernel's; a true neighbour can be missed only if the filter misplaces it by more than 24 ranks. */
+ *           kernel's; a true neighbour can be missed only if the filter misplaces it by more than 24 ranks.
+ * bits 8-9: L2 row prefetch in the search kernel (cp.async.bulk.prefetch.L2, result-identical): 0 = automatic,
+ *           1 = off, 2 = the rows of a pop that wait for a later gather batch, 3 = those + the rows of the
+ *           predicted next pop's neighbours. */
 ZVDB_API int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant);
 
 /* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */

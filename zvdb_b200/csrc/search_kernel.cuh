@@ -64,6 +64,9 @@ struct SearchParams {
     uint32_t *gbitmap;       // VIS_BITMAP: [gridDim.x][bm_words] visited bitmaps in global memory, all zero between queries
     uint32_t *glog;          // VIS_BITMAP: [gridDim.x][log_cap] ids whose bit is set, so the bitmap can be wiped
     uint32_t bm_words, log_cap;
+    // L2 row prefetch (cp.async.bulk.prefetch.L2): bit 0 = rows of the current pop that wait for a later
+    // gather batch, bit 1 = rows of the predicted next pop's neighbours. Changes no result or counter.
+    uint32_t prefetch;
 };
 
 enum : int { kMetricL2 = 0, kMetricCos = 1, kMetricDot = 2 };
@@ -182,6 +185,17 @@ __device__ __forceinline__ float rows_distance(const float4 *__restrict__ arena,
     }
     transposed_reduce<U>(acc, lane, 16);
     return finish_distance<METRIC>(acc[0]);
+}
+
+// Ask for one whole arena row to be brought into L2, one request per 128-byte line, no register and no
+// scoreboard behind it (fire and forget). Per-lane addresses: the bulk form (cp.async.bulk.prefetch.L2)
+// takes its address from a uniform register and compiles to a lane-by-lane loop, ~7 issue slots per row.
+template <int CPL>
+__device__ __forceinline__ void prefetch_row_l2(const float4 *__restrict__ arena, uint32_t row_chunks, uint32_t id) {
+    const float4 *row = arena + static_cast<size_t>(id) * row_chunks;
+#pragma unroll
+    for (int i = 0; i < CPL * 4; ++i)
+        if (static_cast<uint32_t>(i) * 8u < row_chunks) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + i * 8));
 }
 
 // Distance of ONE row, every lane returns it (plain butterfly; same bits as rows_distance).
@@ -464,6 +478,8 @@ search_layer0_kernel(const SearchParams p) {
                 const unsigned vmask = __ballot_sync(kFullMask, valid);
                 if (vmask == 0) continue;
                 const uint32_t nvalid = 32u - __clz(vmask);              // padding sits at the tail of the row
+                if ((p.prefetch & 1u) && valid && lane >= static_cast<uint32_t>(U))   // rows of the later gather batches: start their
+                    prefetch_row_l2<CPL>(arena, p.row_chunks, nb);                        // HBM trip now, next to the first batch's
                 unsigned fmask = 0;
                 bool resolved = false;
                 auto resolve = [&]() {                                    // first use of the atomics' result
@@ -507,6 +523,7 @@ search_layer0_kernel(const SearchParams p) {
             if (fresh) todo[slot_t] = nb;                        // adjacency order kept
             else if (lane - slot_t + t < 32u) todo[lane - slot_t + t] = cur;   // pad todo[t..32) with a hot, valid row id
             nev += t;
+            if ((p.prefetch & 1u) && fresh && slot_t >= static_cast<uint32_t>(U)) prefetch_row_l2<CPL>(arena, p.row_chunks, nb);
             __syncwarp();
 
             // ---- distances (:219) and push (:220) into the pending pool ----
@@ -535,6 +552,9 @@ search_layer0_kernel(const SearchParams p) {
             __syncwarp();
             }
         }
+        // The adjacency row of the predicted next pop has landed by now: start its neighbours' rows towards L2
+        // while this pop's pushes are filed and the next pop is chosen.
+        if ((p.prefetch & 2u) && pref_nb != kInvalidId) prefetch_row_l2<CPL>(arena, p.row_chunks, pref_nb);
     }
 
     // ---- result: stable sort of the popped entries by distance over pop order (hnsw.zig:227-233) ----

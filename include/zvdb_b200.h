@@ -215,9 +215,9 @@ ZVDB_API int zvdb_sync_device(zvdb_index *ix);
  *           hi*hi TF32 product (scores good to ~2^-11 relative, a third of the tensor work), k+24 candidates
  *           are then re-ranked exactly. Returned distances are still exact and bit-identical to the search
  *           kernel's; a true neighbour can be missed only if the filter misplaces it by more than 24 ranks.
- * bits 8-9: L2 row prefetch in the search kernel (cp.async.bulk.prefetch.L2, result-identical): 0 = automatic,
- *           1 = off, 2 = the rows of a pop that wait for a later gather batch, 3 = those + the rows of the
- *           predicted next pop's neighbours. */
+ * bits 8-10: L2 prefetch in the search kernel (prefetch.global.L2, result-identical): 0 = automatic, 1 = off,
+ *           2 = the vector rows of a pop that wait for a later gather batch, 3 = the adjacency rows of the neighbours
+ *           a pop evaluates (one of them is usually the next pop), 4 = both. */
 ZVDB_API int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant);
 
 /* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */

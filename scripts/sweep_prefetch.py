@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""K1 A/B on one B200: L2 row prefetch off / pop / pop + next pop (variant bits 8-9), per ef, on the
+"""K1 A/B on one B200: L2 prefetch off / rows / adjacency / both (variant bits 8-10), per ef, on the
 reference-insert and the quality graph (1M x 128) and, with `c3`, on 1M x 768 cosine M=32. Checks that ids,
 distances and counters are identical across modes. One JSON line per (graph, ef, mode). Not product code."""
 import json, sys, time
@@ -28,7 +28,7 @@ for graph in (("quality",) if c3 else ("reference", "quality")):
     print(f"# {graph} built in {time.time()-t0:.1f}s", flush=True)
     for ef in ((100, 200) if c3 else (32, 64, 128, 256, 512)):
         base = None
-        for mode in (1, 2, 3):
+        for mode in (1, 2, 3, 4):
             h.set_kernel_variant(mode << 8)
             run = lambda: h.search_batch_device(dq.data_ptr(), nq, k, ef, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(),
                                                 d_pops.data_ptr(), d_evals.data_ptr(), stream=stream)
@@ -44,6 +44,6 @@ for graph in (("quality",) if c3 else ("reference", "quality")):
             base = base or sig
             ev = d_evals.cpu().numpy().view(np.uint32)
             rowb = ((dim + 31) // 32) * 128
-            print(json.dumps({"graph": graph, "dim": dim, "m": m, "ef": ef, "prefetch": ["", "off", "pop", "pop+next"][mode], "ms": round(ms, 4),
+            print(json.dumps({"graph": graph, "dim": dim, "m": m, "ef": ef, "prefetch": ["", "off", "rows", "adj", "rows+adj"][mode], "ms": round(ms, 4),
                               "qps": round(nq / ms * 1e3), "alg_gbs": round(float(ev.sum()) * rowb / ms / 1e6, 1), "identical_to_off": same}), flush=True)
     h.deinit()

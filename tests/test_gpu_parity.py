@@ -262,7 +262,7 @@ def test_search_bit_exact_vs_oracle(zv, oracle, n, dim, m, k, ef):
 
 
 @pytest.mark.parametrize("warps", [0b0101, 0b0110, 0b1001, 0b1010,     # {smem hash, global bitmap} x {narrow, wide}
-                                   0x105, 0x205, 0x305, 0x109, 0x209, 0x309])   # x L2 row prefetch {off, pop, pop + next pop}
+                                   0x105, 0x305, 0x405, 0x109, 0x209, 0x309, 0x409])   # x L2 prefetch {off, rows, adjacency, both}
 def test_kernel_variant_does_not_change_results(zv, oracle, warps):
     X, h, adj = _build_pair(zv, oracle, 6000, 128, 16, 43)
     Q = _gauss(300, 128, 44)

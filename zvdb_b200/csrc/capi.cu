@@ -97,7 +97,7 @@ struct zvdb_index {
     bool descent = false;           // off = the reference's search (entry_point, layer 0 only)
     uint32_t variant = 0;           // 0 automatic, 1 narrow, 2 wide (tuning/testing)
     uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap
-    uint32_t prefetch_mode = 0;     // K1 L2 row prefetch: 0 automatic, 1 off, 2 later batches of the pop, 3 + the predicted next pop
+    uint32_t prefetch_mode = 0;     // K1 L2 prefetch: 0 automatic, else 1 + bits (bit 0 rows of a pop's later batches, bit 1 adjacency rows of evaluated neighbours)
     uint32_t bf_mode = 0;           // K4: 0 automatic (CTA pairs), 1 single CTAs, 2 CTA pairs
     uint32_t bf_epilogue = 0;       // K4: 0 automatic (append-and-compact when it applies), 1 sorted lists + cooperative insertion
     bool bf_filter = false;         // K4: single-product TF32 GEMM as a candidate filter (approximate) instead of 3xTF32
@@ -313,12 +313,11 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
         return fail(ZVDB_ERR_UNSUPPORTED, buf);
     }
     p.slots = static_cast<uint32_t>(slots); p.hash_words = static_cast<uint32_t>(slots);
-    // L2 row prefetch. Measured on B200, 1M x 128 (profiles/r01_k1_prefetch_ab.jsonl): the rows of a pop's later
-    // gather batches requested next to the first batch give +2..4 % in bitmap mode on a graph that reaches every
-    // row (ef >= 128), cost 2 % of issue slots in shared-hash mode, and prefetching the predicted next pop's rows
-    // loses everywhere. Automatic = bitmap mode with rows of at most 1 KiB (wider rows are bandwidth bound).
-    p.prefetch = ix->prefetch_mode == 0 ? ((vis == kVisGlobalBitmap && cpl <= 2) ? 1u : 0u)
-                                        : (ix->prefetch_mode == 1 ? 0u : (ix->prefetch_mode == 2 ? 1u : 3u));
+    // L2 prefetch, automatic = the rows of a pop's later gather batches, in bitmap mode with rows of at most 1 KiB
+    // (+2..4 % on a graph that reaches every row; wider rows are bandwidth bound); off in shared-hash mode (small
+    // ef: the extra issue slots cost 1-2 %). Prefetching the evaluated neighbours' adjacency rows measured no gain
+    // anywhere and stays a variant. A/B: profiles/r01_k1_prefetch_ab.jsonl.
+    p.prefetch = ix->prefetch_mode == 0 ? ((vis == kVisGlobalBitmap && cpl <= 2) ? 1u : 0u) : ix->prefetch_mode - 1u;
     p.cand_cap = static_cast<uint32_t>(cand_cap);
     // One warp per query. When shared memory already caps residency at <= 16 warps per SM, use the
     // variant that keeps twice as many row loads in flight per warp (more registers per thread).
@@ -1285,9 +1284,9 @@ int zvdb_sync_device(zvdb_index *ix) {
 int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
     const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u, bfm = (variant >> 4) & 3u;
-    if (width > 2 || vis > 2 || bfm > 2 || variant > 1023)
-        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-9 = L2 row prefetch 0 auto/1 off/2 pop/3 pop + next pop");
-    ix->prefetch_mode = (variant >> 8) & 3u;
+    if (width > 2 || vis > 2 || bfm > 2 || variant > 2047 || ((variant >> 8) & 7u) > 4)
+        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-10 = L2 prefetch 0 auto/1 off/2 rows/3 adjacency/4 both");
+    ix->prefetch_mode = (variant >> 8) & 7u;
     ix->variant = width; ix->visited_mode = vis; ix->bf_mode = bfm; ix->bf_filter = (variant >> 6) & 1u; ix->bf_epilogue = (variant >> 7) & 1u;
     return ZVDB_OK;
 }

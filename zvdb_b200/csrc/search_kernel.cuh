@@ -64,8 +64,9 @@ struct SearchParams {
     uint32_t *gbitmap;       // VIS_BITMAP: [gridDim.x][bm_words] visited bitmaps in global memory, all zero between queries
     uint32_t *glog;          // VIS_BITMAP: [gridDim.x][log_cap] ids whose bit is set, so the bitmap can be wiped
     uint32_t bm_words, log_cap;
-    // L2 row prefetch (cp.async.bulk.prefetch.L2): bit 0 = rows of the current pop that wait for a later
-    // gather batch, bit 1 = rows of the predicted next pop's neighbours. Changes no result or counter.
+    // L2 prefetch (prefetch.global.L2, changes no result or counter): bit 0 = the rows of a pop that wait for a
+    // later gather batch (bitmap mode), bit 1 = the adjacency rows of the neighbours a pop evaluates -- one of
+    // them is the next pop whenever the prediction from the window head fails.
     uint32_t prefetch;
 };
 
@@ -160,10 +161,13 @@ __device__ __forceinline__ float rows_distance(const float4 *__restrict__ arena,
     float4 v[U][CPL];
     const float4 *__restrict__ base = arena + lane;
     if (row_chunks == 32u * CPL) {                       // every lane owns CPL chunks (dim a multiple of 128*CPL... the common case)
+        // byte address = base + id * (compile-time row bytes): one IMAD.WIDE per row instead of multiply + 64-bit shift-add
+        const char *__restrict__ bbase = reinterpret_cast<const char *>(base);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+            const float4 *__restrict__ row = reinterpret_cast<const float4 *>(bbase + static_cast<uint64_t>(ids[u]) * (512u * CPL));
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) v[u][c] = __ldg(base + static_cast<size_t>(ids[u]) * row_chunks + 32 * c);
+            for (int c = 0; c < CPL; ++c) v[u][c] = __ldg(row + 32 * c);
         }
     } else {
 #pragma unroll
@@ -196,6 +200,11 @@ __device__ __forceinline__ void prefetch_row_l2(const float4 *__restrict__ arena
 #pragma unroll
     for (int i = 0; i < CPL * 4; ++i)
         if (static_cast<uint32_t>(i) * 8u < row_chunks) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + i * 8));
+}
+
+// Ask for the head of node `id`'s adjacency row (its first 128-byte line: the whole row for m <= 32).
+__device__ __forceinline__ void prefetch_adj_l2(const uint32_t *__restrict__ adj, uint32_t m, uint32_t id) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(adj + static_cast<size_t>(id) * m));
 }
 
 // Distance of ONE row, every lane returns it (plain butterfly; same bits as rows_distance).
@@ -370,12 +379,26 @@ search_layer0_kernel(const SearchParams p) {
     constexpr int U = Unroll<CPL, WIDE>::value;
     constexpr uint32_t LPR = 32 / U;                            // lanes holding the same row after the reduce
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *res = reinterpret_cast<uint64_t *>(smem_raw);     // [ef] popped keys in pop order
-    uint64_t *cand = res + ((p.ef + 1u) & ~1u);                 // [cand_cap] sorted window lives in [h, h+ns); final-sort scratch (keeps todo 16-byte aligned)
-    uint64_t *pool = cand + p.cand_cap;                         // [kPoolCap] pending pushes, unsorted
-    uint32_t *todo = reinterpret_cast<uint32_t *>(pool + kPoolCap);   // [32] unvisited neighbour ids of the current pass (16-byte aligned)
-    uint32_t *rank_ex = todo + 32;                              // [kPoolCap] merge scratch
-    uint32_t *table = rank_ex + kPoolCap;                       // kVisSmemHash: [hash_words]
+    // Two layouts of the same arrays (same total). Bitmap mode: the fixed-size scratch first, at compile-time offsets
+    // (no address arithmetic on the hot path; measured +7..16 % at ef >= 128). Shared-hash mode keeps the lists first:
+    // there the other order pushes the 64-register variants into spills (measured -12..19 %).
+    uint64_t *res, *cand, *pool;
+    uint32_t *todo, *rank_ex, *table;
+    if constexpr (VIS == kVisGlobalBitmap) {
+        pool = reinterpret_cast<uint64_t *>(smem_raw);              // [kPoolCap] pending pushes, unsorted
+        todo = reinterpret_cast<uint32_t *>(pool + kPoolCap);       // [32] unvisited neighbour ids of the current pass (16-byte aligned)
+        rank_ex = todo + 32;                                        // [kPoolCap] merge scratch
+        res = reinterpret_cast<uint64_t *>(rank_ex + kPoolCap);     // [ef] popped keys in pop order
+        cand = res + ((p.ef + 1u) & ~1u);                           // [cand_cap] sorted window lives in [h, h+ns); final-sort scratch
+        table = nullptr;
+    } else {
+        res = reinterpret_cast<uint64_t *>(smem_raw);
+        cand = res + ((p.ef + 1u) & ~1u);                           // (keeps todo 16-byte aligned)
+        pool = cand + p.cand_cap;
+        todo = reinterpret_cast<uint32_t *>(pool + kPoolCap);
+        rank_ex = todo + 32;
+        table = rank_ex + kPoolCap;                                 // [hash_words] exact visited set, open addressing
+    }
     uint32_t *bitmap = VIS == kVisGlobalBitmap ? p.gbitmap + static_cast<size_t>(blockIdx.x) * p.bm_words : nullptr;
     uint32_t *vlog = VIS == kVisGlobalBitmap ? p.glog + static_cast<size_t>(blockIdx.x) * p.log_cap : nullptr;
 
@@ -428,9 +451,12 @@ search_layer0_kernel(const SearchParams p) {
         uint64_t pk = ~0ull;
         if (lane < npool) pk = pool[lane];
         if (lane + 32 < npool) pk = min(pk, pool[lane + 32]);
-        uint64_t pmin = pk;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) pmin = min(pmin, shfl_xor_u64(pmin, off));
+        // warp minimum of the 64-bit keys by two 32-bit REDUX steps (distance word, then id among its holders)
+        // instead of five 64-bit shuffle levels: the pop selection sits on every pop's critical path
+        const uint32_t pk_d = static_cast<uint32_t>(pk >> 32);
+        const uint32_t pmin_d = __reduce_min_sync(kFullMask, pk_d);
+        const uint32_t pmin_i = __reduce_min_sync(kFullMask, pk_d == pmin_d ? static_cast<uint32_t>(pk) : kInvalidId);
+        const uint64_t pmin = (static_cast<uint64_t>(pmin_d) << 32) | pmin_i;
         const uint64_t head = ns > 0 ? cand[h] : ~0ull;
         const uint64_t cur_key = min(head, pmin);
         if (cur_key == ~0ull) break;                             // candidates.count() == 0
@@ -480,6 +506,7 @@ search_layer0_kernel(const SearchParams p) {
                 const uint32_t nvalid = 32u - __clz(vmask);              // padding sits at the tail of the row
                 if ((p.prefetch & 1u) && valid && lane >= static_cast<uint32_t>(U))   // rows of the later gather batches: start their
                     prefetch_row_l2<CPL>(arena, p.row_chunks, nb);                        // HBM trip now, next to the first batch's
+                if ((p.prefetch & 2u) && valid) prefetch_adj_l2(p.adj, p.m, nb);
                 unsigned fmask = 0;
                 bool resolved = false;
                 auto resolve = [&]() {                                    // first use of the atomics' result
@@ -493,14 +520,12 @@ search_layer0_kernel(const SearchParams p) {
                 // in (the reference's near-tree): there the gather waits for the visited test after all.
                 if (nvalid <= 2) { resolve(); if (fmask == 0) continue; }
                 constexpr unsigned kChunkMask = (U == 32) ? ~0u : ((1u << U) - 1u);
+                const uint32_t nb_row = valid ? nb : cur;                 // hot, valid row for the padding lanes
                 for (uint32_t c0 = 0; c0 < nvalid; c0 += U) {
                     if (resolved && ((fmask >> c0) & kChunkMask) == 0) continue;
                     uint32_t ids[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const uint32_t x = __shfl_sync(kFullMask, nb, c0 + u);
-                        ids[u] = x == kInvalidId ? cur : x;               // hot, valid row for the padding
-                    }
+                    for (int u = 0; u < U; ++u) ids[u] = __shfl_sync(kFullMask, nb_row, c0 + u);
                     const float d = rows_distance<CPL, METRIC, U>(arena, p.row_chunks, ids, qv, lane);
                     if (!resolved) { resolve(); if (((fmask >> c0) & kChunkMask) == 0) continue; }
                     const uint32_t j = c0 + lane / LPR;                   // the neighbour slot whose row this lane holds
@@ -523,7 +548,7 @@ search_layer0_kernel(const SearchParams p) {
             if (fresh) todo[slot_t] = nb;                        // adjacency order kept
             else if (lane - slot_t + t < 32u) todo[lane - slot_t + t] = cur;   // pad todo[t..32) with a hot, valid row id
             nev += t;
-            if ((p.prefetch & 1u) && fresh && slot_t >= static_cast<uint32_t>(U)) prefetch_row_l2<CPL>(arena, p.row_chunks, nb);
+            if ((p.prefetch & 2u) && fresh) prefetch_adj_l2(p.adj, p.m, nb);
             __syncwarp();
 
             // ---- distances (:219) and push (:220) into the pending pool ----
@@ -552,9 +577,6 @@ search_layer0_kernel(const SearchParams p) {
             __syncwarp();
             }
         }
-        // The adjacency row of the predicted next pop has landed by now: start its neighbours' rows towards L2
-        // while this pop's pushes are filed and the next pop is chosen.
-        if ((p.prefetch & 2u) && pref_nb != kInvalidId) prefetch_row_l2<CPL>(arena, p.row_chunks, pref_nb);
     }
 
     // ---- result: stable sort of the popped entries by distance over pop order (hnsw.zig:227-233) ----

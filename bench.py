@@ -302,23 +302,25 @@ def run_ours(args):
         h.search_batch_device(dq[b].data_ptr(), nq, k, e, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(),
                               d_pops.data_ptr(), d_evals.data_ptr(), id_stride=world, id_base=rank, stream=stream)
 
-    def step(b, e=None, q=None):
-        """One pass of the hot path over query batch b (device-resident unless q is given)."""
+    def step(b, e=None, q=None, out=None):
+        """One pass of the hot path over query batch b (device-resident unless q is given; merged results into
+        `out` = (ids, dist, counts) tensors when given -- page-locked host tensors are valid kernel arguments)."""
         e = ef_shard if e is None else e
         q = dq[b] if q is None else q
+        o_ids, o_dist, o_cnt = out if out is not None else ((m_ids, m_dist, m_cnt) if world > 1 else (d_ids, d_dist, d_cnt))
         if world == 1:
             h.search_batch_device(q.data_ptr(), nq, k, e, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(),
                                   d_pops.data_ptr(), d_evals.data_ptr(), stream=stream)
             launches[0] += 1
         elif args.exchange == "p2p":
-            backend.search_exchange(q, nq, k, e, out=(m_ids, m_dist, m_cnt))      # search(+peer stores), signal, merge
+            backend.search_exchange(q, nq, k, e, out=(o_ids, o_dist, o_cnt))      # search(+peer stores), signal, merge
             launches[0] += 3
         else:
             zvdb_b200._lib.check(zvdb_b200.lib().zvdb_search_batch_packed_device(h._h, q.data_ptr(), nq, k, e, blk.data_ptr(),
                                                                                  world, rank, stream))
             dist.all_gather_into_tensor(gathered, blk)
-            zvdb_b200._lib.check(zvdb_b200.lib().zvdb_merge_topk_packed_device(gathered.data_ptr(), world, nq, k, m_dist.data_ptr(),
-                                                                               m_ids.data_ptr(), m_cnt.data_ptr(), stream))
+            zvdb_b200._lib.check(zvdb_b200.lib().zvdb_merge_topk_packed_device(gathered.data_ptr(), world, nq, k, o_dist.data_ptr(),
+                                                                               o_ids.data_ptr(), o_cnt.data_ptr(), stream))
             launches[0] += 2
 
     def barrier():
@@ -438,16 +440,13 @@ def run_ours(args):
     h_ids = torch.empty((nq, k), dtype=torch.int64).pin_memory()
     h_dist = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     h_cnt = torch.empty(nq, dtype=torch.int32).pin_memory()
-    if world > 1:
-        q_dev = torch.empty((nq, args.dim), dtype=torch.float32, device=dev)
 
     def e2e_step(b):
         if world == 1:      # the reference-facing call: zvdb_search_batch on HOST pointers
             h.search_batch_ptr(hq[b].data_ptr(), nq, args.dim, k, ef, h_ids.data_ptr(), h_dist.data_ptr(), h_cnt.data_ptr())
-        else:               # every rank: H2D of the batch, sharded search + exchange + merge, D2H of the merged top-k
-            q_dev.copy_(hq[b], non_blocking=True)
-            step(b, q=q_dev)
-            h_ids.copy_(m_ids, non_blocking=True); h_dist.copy_(m_dist, non_blocking=True); h_cnt.copy_(m_cnt, non_blocking=True)
+        else:               # every rank: the sharded step with page-locked HOST tensors as its query and result buffers --
+            #                 the search kernel reads the batch over PCIe, the merge kernel writes the top-k back
+            step(b, q=hq[b], out=(h_ids, h_dist, h_cnt))
             torch.cuda.current_stream().synchronize()
 
     for w in range(args.warmup):
@@ -458,6 +457,16 @@ def run_ours(args):
         e2e_step(s_ % QUERY_BATCHES)
     barrier()
     e_dt = torch.tensor([time.perf_counter() - t_e], dtype=torch.float64, device=dev)
+    staged_qps = None
+    if world == 1:          # A/B: the same call with the copies staged through device buffers (chunked copy pipeline)
+        h.set_kernel_variant(args.variant | 0x800)
+        for w in range(args.warmup):
+            e2e_step(w % QUERY_BATCHES)
+        t_s = time.perf_counter()
+        for s_ in range(args.steps):
+            e2e_step(s_ % QUERY_BATCHES)
+        staged_qps = nq * args.steps / (time.perf_counter() - t_s)
+        h.set_kernel_variant(args.variant)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed region + e2e loop (200 ms period)"
@@ -465,8 +474,10 @@ def run_ours(args):
         dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
     e2e = {"value": nq * args.steps / float(e_dt.item()), "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4 * world,
            "d2h_bytes_per_step": (nq * k * 12 + nq * 4) * world,
-           "api": "zvdb_search_batch (host pointers)" if world == 1 else
-                  f"per rank: pinned H2D + zvdb_search_batch_{'exchange' if args.exchange == 'p2p' else 'packed_device + all_gather + merge'} + D2H"}
+           "api": "zvdb_search_batch (page-locked host pointers; the kernel reads the batch from and writes the results to host memory)" if world == 1 else
+                  f"per rank: zvdb_search_batch_{'exchange' if args.exchange == 'p2p' else 'packed_device + all_gather + merge'} on page-locked host query/result buffers (read and written by the kernels over PCIe)"}
+    if staged_qps is not None:
+        e2e["staged_copies_qps"] = staged_qps
     if world > 1:
         tb = torch.tensor([float(np.mean(bytes_per_batch))], dtype=torch.float64, device=dev)
         dist.all_reduce(tb)                      # algorithmic bytes of the whole job (all shards)

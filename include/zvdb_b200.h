@@ -217,7 +217,9 @@ ZVDB_API int zvdb_sync_device(zvdb_index *ix);
  *           kernel's; a true neighbour can be missed only if the filter misplaces it by more than 24 ranks.
  * bits 8-10: L2 prefetch in the search kernel (prefetch.global.L2, result-identical): 0 = automatic, 1 = off,
  *           2 = the vector rows of a pop that wait for a later gather batch, 3 = the adjacency rows of the neighbours
- *           a pop evaluates (one of them is usually the next pop), 4 = both. */
+ *           a pop evaluates (one of them is usually the next pop), 4 = both.
+ * bit 11:   zvdb_search_batch with page-locked caller buffers: 0 = the kernel reads the queries from and writes the
+ *           results to host memory directly (no copies), 1 = stage through device buffers (chunked copy pipeline). */
 ZVDB_API int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant);
 
 /* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */

@@ -97,6 +97,7 @@ struct zvdb_index {
     bool descent = false;           // off = the reference's search (entry_point, layer 0 only)
     uint32_t variant = 0;           // 0 automatic, 1 narrow, 2 wide (tuning/testing)
     uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap
+    bool stage_host_buffers = false; // zvdb_search_batch: always copy through device staging buffers (variant bit 11; A/B against zero-copy)
     uint32_t prefetch_mode = 0;     // K1 L2 prefetch: 0 automatic, else 1 + bits (bit 0 rows of a pop's later batches, bit 1 adjacency rows of evaluated neighbours)
     uint32_t bf_mode = 0;           // K4: 0 automatic (CTA pairs), 1 single CTAs, 2 CTA pairs
     uint32_t bf_epilogue = 0;       // K4: 0 automatic (append-and-compact when it applies), 1 sorted lists + cooperative insertion
@@ -1284,9 +1285,9 @@ int zvdb_sync_device(zvdb_index *ix) {
 int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
     const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u, bfm = (variant >> 4) & 3u;
-    if (width > 2 || vis > 2 || bfm > 2 || variant > 2047 || ((variant >> 8) & 7u) > 4)
-        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-10 = L2 prefetch 0 auto/1 off/2 rows/3 adjacency/4 both");
-    ix->prefetch_mode = (variant >> 8) & 7u;
+    if (width > 2 || vis > 2 || bfm > 2 || variant > 4095 || ((variant >> 8) & 7u) > 4)
+        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-10 = L2 prefetch 0 auto/1 off/2 rows/3 adjacency/4 both, bit 11 = stage page-locked host buffers through device copies");
+    ix->prefetch_mode = (variant >> 8) & 7u; ix->stage_host_buffers = (variant >> 11) & 1u;
     ix->variant = width; ix->visited_mode = vis; ix->bf_mode = bfm; ix->bf_filter = (variant >> 6) & 1u; ix->bf_epilogue = (variant >> 7) & 1u;
     return ZVDB_OK;
 }
@@ -1338,6 +1339,28 @@ int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_
     if (dim != ix->g.dim) return fail(ZVDB_ERR_DIM_MISMATCH, "Mismatched dimensions in distance calculation");
     int rc = sync_device_locked(ix);
     if (rc) return rc;
+    // Page-locked, device-mapped caller buffers (zvdb_alloc_host, cudaHostAlloc, cudaHostRegister): no staging at all.
+    // The search kernel reads each query straight from host memory when its warp starts (one 16-byte load per lane,
+    // ~2 us over PCIe against ~100 us of search per query) and writes its k results straight back, so both
+    // transfers ride under the compute of the other ~4 700 resident queries: one launch, no copy calls.
+    auto mapped = [](const void *ptr, void **dptr) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+        *dptr = a.devicePointer;
+        return true;
+    };
+    if (!ix->stage_host_buffers) {
+        void *dq = nullptr, *di = nullptr, *dd = nullptr, *dc = nullptr, *dp = nullptr, *de = nullptr;
+        if (mapped(queries, &dq) && mapped(ids, &di) && mapped(dist, &dd) && mapped(counts, &dc) &&
+            (!pops || mapped(pops, &dp)) && (!evals || mapped(evals, &de))) {
+            rc = launch_search(ix, static_cast<const float *>(dq), nq, k, ef, static_cast<uint64_t *>(di), static_cast<float *>(dd),
+                               static_cast<uint32_t *>(dc), static_cast<uint32_t *>(dp), static_cast<uint32_t *>(de), 1, 0, ix->stream);
+            if (rc) return rc;
+            ZV_CUDA(cudaStreamSynchronize(ix->stream));
+            return ZVDB_OK;
+        }
+    }
     ZV_CUDA(ix->q_buf.reserve(nq * dim));
     ZV_CUDA(ix->ids_buf.reserve(nq * k));
     ZV_CUDA(ix->dist_buf.reserve(nq * k));

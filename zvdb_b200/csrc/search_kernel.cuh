@@ -119,6 +119,30 @@ __device__ __forceinline__ float lane_partial(uint64_t acc) {
     float a0, a1; unpack2(acc, a0, a1); return __fadd_rn(a0, a1);
 }
 
+// One query -> registers, chunked like an arena row (lane l owns 16-byte chunks l, l+32, ...), packed in pairs
+// for the f32x2 pipe, zero padded. One 16-byte load per chunk when the row allows it: the query may live in
+// page-locked HOST memory (zvdb_search_batch's zero-copy path), where every load instruction is a PCIe read.
+template <int CPL>
+__device__ __forceinline__ void load_query(Chunk2 (&qv)[CPL], const float *__restrict__ qp, uint32_t dim, uint32_t lane) {
+    if ((dim & 3u) == 0 && (reinterpret_cast<uintptr_t>(qp) & 15u) == 0) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const uint32_t i = (lane + 32u * c) * 4u;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < dim) v = *reinterpret_cast<const float4 *>(qp + i);
+            qv[c].xy = pack2(v.x, v.y); qv[c].zw = pack2(v.z, v.w);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const uint32_t i = (lane + 32u * c) * 4u;
+            const float x = i + 0 < dim ? qp[i + 0] : 0.f, y = i + 1 < dim ? qp[i + 1] : 0.f;
+            const float z = i + 2 < dim ? qp[i + 2] : 0.f, w = i + 3 < dim ? qp[i + 3] : 0.f;
+            qv[c].xy = pack2(x, y); qv[c].zw = pack2(z, w);
+        }
+    }
+}
+
 template <int METRIC>
 __device__ __forceinline__ float finish_distance(float s) {
     if (METRIC == kMetricCos) return __fsub_rn(1.0f, s);
@@ -317,16 +341,7 @@ __global__ void __launch_bounds__(128) descend_kernel(const SearchParams p) {
     if (q >= p.nq) return;
     const float4 *__restrict__ arena = p.arena;
     Chunk2 qv[CPL];
-    {
-        const float *qp = p.queries + static_cast<size_t>(q) * p.dim;
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const uint32_t i = (lane + 32u * c) * 4u;
-            const float x = i + 0 < p.dim ? qp[i + 0] : 0.f, y = i + 1 < p.dim ? qp[i + 1] : 0.f;
-            const float z = i + 2 < p.dim ? qp[i + 2] : 0.f, w = i + 3 < p.dim ? qp[i + 3] : 0.f;
-            qv[c].xy = pack2(x, y); qv[c].zw = pack2(z, w);
-        }
-    }
+    load_query<CPL>(qv, p.queries + static_cast<size_t>(q) * p.dim, p.dim, lane);
     uint32_t entry = p.descent_start, ndesc = 0;
     float d0 = row_distance<CPL, METRIC>(arena, p.row_chunks, entry, qv, lane);
     for (uint32_t layer = p.max_level; layer >= 1; --layer) {
@@ -409,16 +424,7 @@ search_layer0_kernel(const SearchParams p) {
     for (uint32_t q = blockIdx.x; q < p.nq; q += gridDim.x) {   // persistent when gridDim.x < nq
     // Query -> registers, chunked like an arena row, packed in pairs for the f32x2 pipe.
     Chunk2 qv[CPL];
-    {
-        const float *qp = p.queries + static_cast<size_t>(q) * p.dim;
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const uint32_t i = (lane + 32u * c) * 4u;
-            const float x = i + 0 < p.dim ? qp[i + 0] : 0.f, y = i + 1 < p.dim ? qp[i + 1] : 0.f;
-            const float z = i + 2 < p.dim ? qp[i + 2] : 0.f, w = i + 3 < p.dim ? qp[i + 3] : 0.f;
-            qv[c].xy = pack2(x, y); qv[c].zw = pack2(z, w);
-        }
-    }
+    load_query<CPL>(qv, p.queries + static_cast<size_t>(q) * p.dim, p.dim, lane);
     if (VIS == kVisSmemHash) {
         for (uint32_t i = lane; i < p.slots; i += 32) table[i] = kInvalidId;
     }

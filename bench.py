@@ -511,6 +511,13 @@ def run_ours(args):
         got = d_ids.cpu().numpy().view(np.uint64)[:sample]
         same = float((got == ref["ids"].astype(np.uint64)).mean())
         ev_same = bool(np.array_equal(d_evals.cpu().numpy().view(np.uint32)[:sample], ref["evals"]))
+        # bit-exact check against the oracle in the kernel's own arithmetic and tie order (DIST_TREE / HEAP_DET): the
+        # timed run above is the reference's arithmetic (sequential sum, Zig heap), equal up to 1e-5 near-ties
+        chk = min(500, sample)
+        det = O.search_graph(X, adj, Qs[0][:chk], ef, k, dist_mode=O.DIST_TREE, heap_mode=O.HEAP_DET, **kw)
+        det_ids = bool(np.array_equal(got[:chk], det["ids"].astype(np.uint64)))
+        det_dist = bool(np.array_equal(d_dist.cpu().numpy()[:chk].view(np.uint32), det["dist"].view(np.uint32)))
+        det_evals = bool(np.array_equal(d_evals.cpu().numpy().view(np.uint32)[:chk], det["evals"]))
         # (i) one thread, (iii) every thread behind one global lock (the reference's real
         # behaviour, hnsw.zig:195-196) on a smaller slice of the same sample
         small = Qs[0][:max(64, sample // 8)]
@@ -519,7 +526,8 @@ def run_ours(args):
         cpu = {"value": sample / c_dt, "unit": "queries/s", "cores": O.max_threads(), "kind": "port",
                "sample": f"first {sample} queries of batch 0, same graph/ef/k, one query per thread, no lock",
                "one_thread_qps": one, "global_lock_qps_all_threads": lock,
-               "ids_equal_frac_vs_gpu": same, "evals_equal_vs_gpu": ev_same}
+               "ids_equal_frac_vs_gpu": same, "evals_equal_vs_gpu": ev_same,
+               "bit_exact_vs_oracle_tree_det": {"queries": chk, "ids": det_ids, "dist_bits": det_dist, "evals": det_evals}}
 
     peak, peak_src = load_peaks()
     avg_kernel_s = float(np.mean(kern_ms)) * 1e-3

@@ -185,9 +185,11 @@ ZVDB_API int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq
                                uint32_t k, uint32_t ef, uint64_t *ids, float *dist, uint32_t *counts,
                                uint32_t *pops, uint32_t *evals);
 
-/* Page-locked host memory for query / result buffers. zvdb_search_batch accepts any host memory; with
- * page-locked buffers the host<->device copies run asynchronously at full PCIe rate and large batches
- * are pipelined (copy-in, kernel and copy-out of successive chunks overlap on two streams). A Zig
+/* Page-locked, device-mapped host memory for query / result buffers. zvdb_search_batch accepts any host memory
+ * (pageable buffers are staged through device copies); when queries, ids, dist and counts (and pops / evals if
+ * given) are all page-locked, the call makes NO copies: the search kernel reads each query from host memory when
+ * its warp starts and writes the k results straight back, so both transfers ride under the compute of the other
+ * resident queries (1M x 128, 10 000 queries: 19.8 M QPS against 18.0 M through the staged copy pipeline). A Zig
  * caller wraps these two in a std.mem.Allocator. NULL on failure (zvdb_last_error). */
 ZVDB_API void *zvdb_alloc_host(size_t bytes);
 ZVDB_API void zvdb_free_host(void *p);

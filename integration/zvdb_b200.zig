@@ -143,7 +143,8 @@ pub fn HNSW(comptime T: type) type {
             try check(zvdb_load(h, path.ptr));
         }
 
-        /// Page-locked buffers for searchBatch (asynchronous copies, pipelined large batches).
+        /// Page-locked, device-mapped buffers for searchBatch: the search kernel reads the queries from and writes the
+        /// results to them directly (no host<->device copy calls).
         pub fn allocPinned(comptime E: type, n: usize) ![]E {
             const p = zvdb_alloc_host(n * @sizeOf(E)) orelse return error.OutOfMemory;
             return @as([*]E, @ptrCast(@alignCast(p)))[0..n];

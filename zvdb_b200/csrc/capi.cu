@@ -1,5 +1,6 @@
 // capi.cu -- libzvdb_b200.so: the C ABI of include/zvdb_b200.h over the host graph (insert) and
 // the sm_100a kernels (search, scatter, merge). No CPU search path exists in this library.
+#include <cstring>
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -77,6 +78,8 @@ struct zvdb_index {
     cudaStream_t stream_in = nullptr; // owned; carries the pipeline's host-to-device copies, so chunk c+2 arrives while chunk c still runs
     cudaEvent_t in_ev[8] = {};      // chunk c of the query batch is on the device
     cudaEvent_t bitmap_ev = nullptr; // last kernel that used the shared visited bitmaps
+    unsigned char *h_stage = nullptr; // owned, page-locked + device-mapped: small pageable batches (the single search call) go through it
+    size_t h_stage_cap = 0;
     float *d_arena = nullptr;       // [cap_rows][row_floats]
     uint32_t *d_adj = nullptr;      // [cap_rows][m]
     uint64_t cap_rows = 0, n_dev = 0;
@@ -771,6 +774,7 @@ void zvdb_destroy(zvdb_index *ix) {
     for (int i = 0; i < 8; ++i) if (ix->in_ev[i]) cudaEventDestroy(ix->in_ev[i]);
     if (ix->bitmap_ev) cudaEventDestroy(ix->bitmap_ev);
     cudaFree(ix->d_arena); cudaFree(ix->d_adj);
+    if (ix->h_stage) cudaFreeHost(ix->h_stage);
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
     ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_();
     ix->d_level.free_(); ix->d_upper_base.free_(); ix->d_upper_adj.free_(); ix->seeds_buf.free_();
@@ -1358,6 +1362,38 @@ int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_
                                static_cast<uint32_t *>(dc), static_cast<uint32_t *>(dp), static_cast<uint32_t *>(de), 1, 0, ix->stream);
             if (rc) return rc;
             ZV_CUDA(cudaStreamSynchronize(ix->stream));
+            return ZVDB_OK;
+        }
+    }
+    // Small batches in pageable memory -- above all the reference's own call, search(query, k) -- go through one
+    // page-locked, device-mapped staging block owned by the index: two host memcpys around ONE kernel launch that
+    // reads the queries and writes the results in that block, instead of five cudaMemcpyAsync calls around it.
+    {
+        auto up = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+        const size_t qb = up(nq * dim * sizeof(float)), ib = up(nq * k * sizeof(uint64_t)), db = up(nq * k * sizeof(float)), cb = up(nq * sizeof(uint32_t));
+        const size_t total = qb + ib + db + 3 * cb;
+        if (!ix->stage_host_buffers && total <= (1u << 20)) {
+            if (total > ix->h_stage_cap) {
+                if (ix->h_stage) { ZV_CUDA(cudaStreamSynchronize(ix->stream)); cudaFreeHost(ix->h_stage); ix->h_stage = nullptr; ix->h_stage_cap = 0; }
+                const size_t cap = std::max<size_t>(total, 64u << 10);
+                ZV_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ix->h_stage), cap, cudaHostAllocMapped));
+                ix->h_stage_cap = cap;
+            }
+            unsigned char *hb = ix->h_stage, *dbase = nullptr;
+            ZV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&dbase), hb, 0));
+            const size_t o_ids = qb, o_dist = qb + ib, o_cnt = o_dist + db, o_pops = o_cnt + cb, o_evals = o_pops + cb;
+            std::memcpy(hb, queries, nq * dim * sizeof(float));
+            rc = launch_search(ix, reinterpret_cast<const float *>(dbase), nq, k, ef, reinterpret_cast<uint64_t *>(dbase + o_ids),
+                               reinterpret_cast<float *>(dbase + o_dist), reinterpret_cast<uint32_t *>(dbase + o_cnt),
+                               pops ? reinterpret_cast<uint32_t *>(dbase + o_pops) : nullptr,
+                               evals ? reinterpret_cast<uint32_t *>(dbase + o_evals) : nullptr, 1, 0, ix->stream);
+            if (rc) return rc;
+            ZV_CUDA(cudaStreamSynchronize(ix->stream));
+            std::memcpy(ids, hb + o_ids, nq * k * sizeof(uint64_t));
+            std::memcpy(dist, hb + o_dist, nq * k * sizeof(float));
+            std::memcpy(counts, hb + o_cnt, nq * sizeof(uint32_t));
+            if (pops) std::memcpy(pops, hb + o_pops, nq * sizeof(uint32_t));
+            if (evals) std::memcpy(evals, hb + o_evals, nq * sizeof(uint32_t));
             return ZVDB_OK;
         }
     }

@@ -325,8 +325,8 @@ class HNSW:
 
 class PinnedArray:
     """A numpy array over page-locked host memory from zvdb_alloc_host (freed by .free() or on collection).
-    Pass `.array` to search_batch-style calls: page-locked buffers are copied asynchronously and large
-    batches are pipelined."""
+    Pass `.array` to search_batch-style calls: with page-locked query and result buffers the search kernel reads
+    and writes them in place (no host<->device copy calls)."""
 
     def __init__(self, shape, dtype):
         self.dtype = np.dtype(dtype)

@@ -236,7 +236,8 @@ def _build_pair(zv, oracle, n, dim, m, seed, metric=0):
 @pytest.mark.parametrize("n,dim,m,k,ef", [
     (10000, 128, 16, 10, 10),     # C1: the reference call, ef = k
     (10000, 128, 16, 10, 64),     # C1 with the config's "ef_search = 64" = search(q,64)[:10]
-    (10000, 128, 16, 10, 512),
+    (10000, 128, 16, 10, 512),    # bitmap mode, popped keys in global scratch
+    (10000, 128, 16, 300, 600),   # ... with a long result list read back from it
     (4000, 3, 16, 5, 20),         # tiny dim (padding lanes)
     (4000, 200, 16, 10, 40),      # dim not a multiple of 128 floats
     (3000, 768, 32, 100, 128),    # C3 shape: 6 chunks per lane, M = 32, k = 100

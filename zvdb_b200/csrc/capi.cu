@@ -86,6 +86,7 @@ struct zvdb_index {
     DevBuf<float> q_buf, dist_buf;
     DevBuf<uint64_t> ids_buf;
     DevBuf<uint32_t> cnt_buf, pops_buf, evals_buf, scat_rows, scat_ids, bitmap_buf, vlog_buf;
+    DevBuf<uint64_t> res_buf;       // bitmap mode: per-CTA popped-key lists
     // K4 (brute force): TF32 hi/lo split of the arena + squared row norms, rebuilt when the rows change
     DevBuf<float> bf_xhi, bf_xlo, bf_xnorm, bf_qhi, bf_qlo;
     DevBuf<uint64_t> bf_part, bf_glists;
@@ -309,7 +310,10 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     // Where the exact visited set lives. On chip while that still leaves >= 20 warps per SM; beyond
     // that a per-CTA bitmap in global memory keeps residency up (one atomicOr per neighbour).
     const int vis = plan_visited(ix, ef);
-    const uint64_t smem = vis == kVisSmemHash ? smem_hash : smem_lists;
+    const uint64_t res_cap = (static_cast<uint64_t>(ef) + 1) & ~1ull;
+    // bitmap mode: the popped-key list moves to per-CTA global scratch when it would cost residency (see the kernel)
+    const bool res_global = vis == kVisGlobalBitmap && ctas_for(smem_lists) < 32;
+    const uint64_t smem = vis == kVisSmemHash ? smem_hash : (res_global ? smem_lists - res_cap * 8 : smem_lists);
     if (smem > ix->smem_optin) {
         char buf[256];
         snprintf(buf, sizeof buf, "search needs %llu bytes of shared memory per query (ef=%u, m=%u); this device allows %zu. Lower ef.",
@@ -343,6 +347,10 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
         }
         const uint64_t log_cap = (bound + 3) & ~3ull;                          // 16-byte aligned logs (read back as uint4)
         ZV_CUDA(ix->vlog_buf.reserve(grid * log_cap));
+        if (res_global) {
+            ZV_CUDA(ix->res_buf.reserve(grid * res_cap));
+            p.gres = ix->res_buf.p; p.res_cap = static_cast<uint32_t>(res_cap);
+        }
         p.gbitmap = ix->bitmap_buf.p; p.glog = ix->vlog_buf.p;
         p.bm_words = static_cast<uint32_t>(bm_words); p.log_cap = static_cast<uint32_t>(log_cap);
     }
@@ -776,7 +784,7 @@ void zvdb_destroy(zvdb_index *ix) {
     cudaFree(ix->d_arena); cudaFree(ix->d_adj);
     if (ix->h_stage) cudaFreeHost(ix->h_stage);
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
-    ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_();
+    ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_(); ix->res_buf.free_();
     ix->d_level.free_(); ix->d_upper_base.free_(); ix->d_upper_adj.free_(); ix->seeds_buf.free_();
     ix->bf_xhi.free_(); ix->bf_xlo.free_(); ix->bf_xnorm.free_(); ix->bf_qhi.free_(); ix->bf_qlo.free_(); ix->bf_part.free_(); ix->bf_glists.free_(); ix->bf_segs.free_(); ix->bf_seg_off.free_();
     delete ix;

@@ -64,6 +64,8 @@ struct SearchParams {
     uint32_t *gbitmap;       // VIS_BITMAP: [gridDim.x][bm_words] visited bitmaps in global memory, all zero between queries
     uint32_t *glog;          // VIS_BITMAP: [gridDim.x][log_cap] ids whose bit is set, so the bitmap can be wiped
     uint32_t bm_words, log_cap;
+    uint64_t *gres;          // VIS_BITMAP: [gridDim.x][res_cap] popped keys in pop order (written once per pop, read by the final sort)
+    uint32_t res_cap;
     // L2 prefetch (prefetch.global.L2, changes no result or counter): bit 0 = the rows of a pop that wait for a
     // later gather batch (bitmap mode), bit 1 = the adjacency rows of the neighbours a pop evaluates -- one of
     // them is the next pop whenever the prediction from the window head fails.
@@ -403,8 +405,12 @@ search_layer0_kernel(const SearchParams p) {
         pool = reinterpret_cast<uint64_t *>(smem_raw);              // [kPoolCap] pending pushes, unsorted
         todo = reinterpret_cast<uint32_t *>(pool + kPoolCap);       // [32] unvisited neighbour ids of the current pass (16-byte aligned)
         rank_ex = todo + 32;                                        // [kPoolCap] merge scratch
-        res = reinterpret_cast<uint64_t *>(rank_ex + kPoolCap);     // [ef] popped keys in pop order
-        cand = res + ((p.ef + 1u) & ~1u);                           // [cand_cap] sorted window lives in [h, h+ns); final-sort scratch
+        // The popped keys are written once per pop and read only by the final sort. When they would push residency
+        // below 32 queries per SM (ef > 256) they go to per-CTA global scratch (L2) instead of shared memory:
+        // ef=512: 9.1 -> 5.0 KB per query, 22 -> 32 resident queries per SM, +20..27 % QPS.
+        uint64_t *lists = reinterpret_cast<uint64_t *>(rank_ex + kPoolCap);
+        if (p.gres) { res = p.gres + static_cast<size_t>(blockIdx.x) * p.res_cap; cand = lists; }
+        else { res = lists; cand = lists + ((p.ef + 1u) & ~1u); }   // [cand_cap] sorted window lives in [h, h+ns); final-sort scratch
         table = nullptr;
     } else {
         res = reinterpret_cast<uint64_t *>(smem_raw);

@@ -26,7 +26,7 @@ for graph in (("quality",) if c3 else ("reference", "quality")):
     else: builder.build_quality_graph(h, X, m)
     h.sync_device()
     print(f"# {graph} built in {time.time()-t0:.1f}s", flush=True)
-    for ef in ((100, 200) if c3 else (32, 64, 128, 256, 512)):
+    for ef in ((100, 200) if c3 else (10, 16, 32, 64, 128, 256, 512)):
         base = None
         for mode in (1, 2, 3, 4):
             h.set_kernel_variant(mode << 8)

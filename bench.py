@@ -72,7 +72,9 @@ def parse_args():
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--ef", type=int, default=64)
     p.add_argument("--m", type=int, default=16)
-    p.add_argument("--graph", default="reference", choices=["reference", "quality"])
+    p.add_argument("--graph", default="reference", choices=["reference", "quality", "incremental"],
+                   help="reference = the reference's insert; quality = GPU builder on exact (GEMM) candidates, O(n^2); "
+                        "incremental = GPU builder on candidates from the index's own search (scales to C4 shards)")
     p.add_argument("--sweep", action="store_true", help="also report the ef sweep 32..512 (untimed extra passes)")
     p.add_argument("--variant", type=int, default=0, help="search kernel variant: 0 auto, 1 narrow, 2 wide")
     p.add_argument("--cpu-sample", type=int, default=2000, help="queries in the CPU-baseline sample")
@@ -262,9 +264,12 @@ def run_ours(args):
     h = zvdb_b200.HNSW(args.m, 200, device=local)
     if args.graph == "reference":
         h.insert_batch(Xs)
-    else:
+    elif args.graph == "quality":
         from zvdb_b200 import builder
         builder.build_quality_graph(h, Xs, args.m)
+    else:
+        from zvdb_b200 import builder
+        builder.build_quality_graph_incremental(h, Xs, args.m, log=log)
     h.sync_device()
     if args.descent:
         h.set_descent(True)
@@ -540,7 +545,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.n}x{args.dim} fp32 L2 synthetic Gaussian, M={args.m}, {nq}-query batch, k={k}, "
                                f"ef={ef}" + (", upper-layer descent on" if args.descent else "") + (f" ({ef_shard} pops/shard, id-sharded over {world} GPUs, exchange={args.exchange})" if world > 1 else ""),
-                   "graph": "reference insert (hnsw.zig:73-170)" if args.graph == "reference" else "quality builder",
+                   "graph": {"reference": "reference insert (hnsw.zig:73-170)", "quality": "quality builder (exact candidates)",
+                             "incremental": "quality builder (search-driven incremental candidates)"}[args.graph],
                    "l2_policy": f"index {args.n * args.dim * 4 / 1e6:.0f} MB > 126 MB L2; {QUERY_BATCHES} query batches rotated",
                    "recall_at_10": recalls[0] if recalls else None,
                    "evals_per_query": float(np.mean(evals_mean)), "pops_per_query": float(np.mean(pops_mean)),

@@ -434,3 +434,33 @@ def test_builder_graph_reaches_useful_recall(zv, oracle):
     rec = np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(Q))])
     assert rec > 0.9, rec
     h.deinit()
+
+
+def test_incremental_builder_is_close_to_the_exact_candidate_builder(zv, oracle):
+    """The search-driven builder (candidates = the index's own search on the growing graph) against the same builder
+    fed exact k-NN candidates: same layout, every row linked and reachable, recall within a few points."""
+    from zvdb_b200 import builder
+    n, dim, m, K = 20000, 64, 16, 48
+    X = _gauss(n, dim, 65)
+    Q = _gauss(200, dim, 66)
+    gt, _ = oracle.bruteforce(X, Q, 10)
+
+    def recall(h):
+        ids, _, _ = h.search_batch(Q, 10, 256)
+        return np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(Q))])
+
+    nn, _ = oracle.bruteforce(X, X, K + 1)
+    exact = zv.HNSW(m, 200)
+    exact.build_from_candidates(X, nn[:, 1:].astype(np.uint32))
+    inc = zv.HNSW(m, 200)
+    stats = builder.build_quality_graph_incremental(inc, X, m, K=K, seed_rows=2048, ef=128, join=4)
+    assert stats["phases"] >= 4 and inc.count() == n and inc.entry_point == 0
+    adj, deg = inc.export_layer(0)
+    assert adj.shape == (n, m) and deg.min() >= 1
+    r_exact, r_inc = recall(exact), recall(inc)
+    assert r_inc >= r_exact - 0.08, (r_exact, r_inc)
+    # searched by the same kernel with the same parity
+    ids, dist, counts, pops, evals = inc.search_batch(Q, 5, 30, counters=True)
+    r = oracle.search_graph(X, adj, Q, 30, 5, dist_mode=oracle.DIST_TREE, heap_mode=oracle.HEAP_DET)
+    assert np.array_equal(ids, r["ids"].astype(np.uint64)) and np.array_equal(evals, r["evals"])
+    exact.deinit(); inc.deinit()

@@ -5,6 +5,12 @@ Candidate generation (approximate k-NN ids) feeds zvdb_build_from_candidates, wh
 Candidates may therefore come from a cheap, inexact source: here a chunked torch GEMM + top-k on
 the GPU (library plumbing, outside every timed region). No reference counterpart: the reference's
 producer is HNSW.insert.
+
+The GEMM source is O(n^2): fine at 1M rows (18 s), out of reach for the 12.5M-row shards of C4.
+`build_quality_graph_incremental` is the scalable source: the index's OWN search kernel produces the
+candidates -- the construction every HNSW uses (a new point's neighbours are what a search of the
+current graph finds, the reference's insert included, hnsw.zig:88-108), run batch-wise over doubling
+prefixes so that every step is one batched search + one builder pass on the GPU.
 """
 from __future__ import annotations
 
@@ -36,3 +42,82 @@ def build_quality_graph(h, X: np.ndarray, m: int, K: int = 64, device=None, chun
     h.build_from_candidates(X, K=K, cand_device_ptr=cand.data_ptr())
     del cand
     torch.cuda.empty_cache()
+
+
+def build_quality_graph_incremental(h, X: np.ndarray, m: int, K: int = 64, seed_rows: int = 131072, ef: int = 0,
+                                    growth: float = 2.0, refine_rounds: int = 2, join: int = 0, query_chunk: int = 1 << 20,
+                                    device=None, log=None):
+    """Fill index `h` with a graph over all rows of X, built prefix by prefix: the first `seed_rows` rows from GEMM
+    candidates, then each new block of rows (the prefix grows by `growth`) is SEARCHED on the current graph
+    (K1, ef = K pops: the popped set is the candidate list, nearest first) and the builder kernels re-link the whole
+    prefix -- new rows get their pruned forward lists, old rows gain the new rows through the reverse-edge step.
+    The rows of one block cannot find each other that way (they are searched on a graph that holds none of them), so
+    `refine_rounds` passes follow: EVERY row is searched on the finished graph and the graph is rebuilt from those
+    candidates (one batched search of n queries + one builder pass per round). With `join` = J > 0 a refinement round
+    also offers every row the neighbour lists of its first J neighbours (the local join of NN-descent), J * m extra
+    candidates per row (K + J * m <= 128).
+    Cost: O(n log n) row evaluations in searches + (2 + refine_rounds) builder passes over n. Returns build statistics."""
+    import time
+    import torch
+    device = device or torch.device("cuda", h.device)
+    n, dim = X.shape
+    K = min(K, 128, max(1, n))
+    ef = max(ef or 4 * K, K)          # pops per construction search; measured at 1M x 128: recall@10 at ef_search=512 is
+    #                                   0.33 / 0.37 / 0.40 for 64 / 128 / 256 pops (GEMM candidates: 0.47), build 4-5 s
+    stream = torch.cuda.current_stream(device).cuda_stream
+    t0 = time.time()
+    n_cur = min(n, max(int(seed_rows), K + 1))
+    join = max(0, min(int(join), (128 - K) // m)) if refine_rounds > 0 else 0
+    KT = K + join * m                                                          # candidate slots per row (row pitch of `cand`)
+    cand = torch.full((n, KT), -1, dtype=torch.int32, device=device)         # 0xFFFFFFFF = padding, tolerated by the builder
+    cand[:n_cur, :K] = knn_candidates_torch(X[:n_cur], K, device)
+    torch.cuda.synchronize(device)
+    h.build_from_candidates(X[:n_cur], K=KT, cand_device_ptr=cand.data_ptr())
+    phases, searched = 1, [0]
+
+    def search_rows(lo, hi):
+        """cand[lo:hi] = what a K-pop search of each row finds on the current graph (nearest first)."""
+        for s in range(lo, hi, query_chunk):
+            e = min(hi, s + query_chunk)
+            q = torch.from_numpy(np.ascontiguousarray(X[s:e], np.float32)).to(device)
+            ids = torch.empty((e - s, K), dtype=torch.int64, device=device)
+            dist = torch.empty((e - s, K), dtype=torch.float32, device=device)
+            cnt = torch.empty(e - s, dtype=torch.int32, device=device)
+            h.search_batch_device(q.data_ptr(), e - s, K, ef, ids.data_ptr(), dist.data_ptr(), cnt.data_ptr(), stream=stream)
+            cand[s:e, :K] = ids.to(torch.int32)                               # unused slots (~0) become 0xFFFFFFFF
+            searched[0] += e - s
+            del q, ids, dist, cnt
+
+    while n_cur < n:
+        n_next = min(n, max(n_cur + 1, int(n_cur * growth)))
+        search_rows(n_cur, n_next)
+        torch.cuda.synchronize(device)
+        h.build_from_candidates(X[:n_next], K=KT, cand_device_ptr=cand.data_ptr())
+        n_cur = n_next
+        phases += 1
+        if log:
+            log(f"[builder] prefix {n_cur} / {n} rows linked ({time.time() - t0:.1f}s)")
+    for r in range(refine_rounds):
+        search_rows(0, n)
+        # keep what the row already has: its current neighbours take the first m candidate slots, the search the rest
+        adj, _ = h.export_layer(0)
+        adj_t = torch.from_numpy(adj.view(np.int32)).to(device)
+        del adj
+        cand[:, :m] = adj_t
+        for s in range(0, n, query_chunk if join else n):                     # local join: neighbours of the first J neighbours
+            if not join:
+                break
+            e = min(n, s + query_chunk)
+            nb = adj_t[s:e, :join]
+            far = adj_t[nb.clamp(min=0).long()]                               # [rows, J, m]
+            far[nb < 0] = -1
+            cand[s:e, K:] = far.reshape(e - s, join * m)
+            del nb, far
+        del adj_t
+        torch.cuda.synchronize(device)
+        h.build_from_candidates(X, K=KT, cand_device_ptr=cand.data_ptr())
+        if log:
+            log(f"[builder] refinement round {r + 1} / {refine_rounds} ({time.time() - t0:.1f}s)")
+    del cand
+    torch.cuda.empty_cache()
+    return {"phases": phases, "refine_rounds": refine_rounds, "rows_searched": searched[0], "seconds": time.time() - t0, "K": K, "ef": ef, "join": join, "growth": growth}

@@ -22,7 +22,8 @@ gt = None
 configs = [("exact", {})] if not skip_exact else []
 import os
 build_efs = [int(x) for x in os.environ.get("ZVDB_BUILD_EF", "128,256,512").split(",")]
-configs += [("incremental", dict(refine_rounds=2, ef=e)) for e in build_efs]
+build_K = int(os.environ.get("ZVDB_BUILD_K", "64"))
+configs += [("incremental", dict(refine_rounds=2, ef=e, K=build_K)) for e in build_efs]
 for name, kw in configs:
     h = zvdb_b200.HNSW(m, 200)
     t0 = time.time()
@@ -30,7 +31,7 @@ for name, kw in configs:
         builder.build_quality_graph(h, X, m)
         stats = {}
     else:
-        stats = builder.build_quality_graph_incremental(h, X, m, K=64, log=lambda s: print("#", s, flush=True), **kw)
+        stats = builder.build_quality_graph_incremental(h, X, m, log=lambda s: print("#", s, flush=True), **kw)
     h.sync_device()
     build_s = time.time() - t0
     if gt is None:      # exact ground truth from the tensor-core brute force (K4)

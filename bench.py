@@ -132,7 +132,7 @@ def load_traffic(graph, n, dim, m, nq, ef):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -145,7 +145,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -474,7 +474,7 @@ def run_ours(args):
         h.set_kernel_variant(args.variant)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = "warm-up + timed region + e2e loop (200 ms period)"
+        clocks["window"] = "warm-up + timed region + e2e loop (50 ms period)"
     if world > 1:
         dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
     e2e = {"value": nq * args.steps / float(e_dt.item()), "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4 * world,

@@ -69,3 +69,41 @@ def test_product_does_not_import_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
                 assert "orc_" not in txt, f
+
+
+def test_header_is_plain_c_and_a_c_caller_links(zv, tmp_path):
+    """The boundary is a C ABI: include/zvdb_b200.h must compile as C (no C++ / torch types) and a C program must
+    link against libzvdb_b200.so and reach an entry point. Without a GPU the create call fails loudly (no CPU path)."""
+    import os
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "zvdb_b200.h"
+int main(void) {
+    zvdb_index *ix = 0;
+    int rc = zvdb_create(&ix, 0, 16, 200, 0, 0);
+    if (rc != 0) { printf("create failed rc=%d: %s\n", rc, zvdb_last_error()); return 3; }
+    float p[4] = {1.f, 2.f, 3.f, 4.f}, q[4] = {1.f, 2.f, 3.f, 5.f}, d[1]; uint64_t id[1]; uint32_t cnt = 0;
+    if (zvdb_insert(ix, p, 4) != 0 || zvdb_search(ix, q, 4, 1, id, d, &cnt) != 0) { printf("%s\n", zvdb_last_error()); return 4; }
+    printf("ok id=%llu d=%g n=%u\n", (unsigned long long)id[0], d[0], cnt);
+    zvdb_destroy(ix);
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.join(root, "zvdb_b200", "lib")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lzvdb_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and run.stdout.startswith("ok id=0 d=1 n=1"), run.stdout + run.stderr
+    else:
+        assert run.returncode == 3 and "create failed" in run.stdout, run.stdout + run.stderr

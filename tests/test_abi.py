@@ -107,3 +107,22 @@ int main(void) {
         assert run.returncode == 0 and run.stdout.startswith("ok id=0 d=1 n=1"), run.stdout + run.stderr
     else:
         assert run.returncode == 3 and "create failed" in run.stdout, run.stdout + run.stderr
+
+
+def test_search_kernels_fit_their_register_budget_without_spills(zv):
+    """Every instantiation of the hot-path kernel must fit the register budget its residency needs (one-warp CTAs:
+    32 per SM -> 64 registers for the narrow variants of rows up to 1 KiB) with no stack frame: a spill in the pop loop
+    cost 12-19 % when it was measured (profiles/r01_k1_experiments.md), so it must not come back unnoticed."""
+    import re
+    import shutil
+    import subprocess
+    from zvdb_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    rows = re.findall(r"Function (\S*search_layer0_kernel\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert len(rows) >= 60, "search_layer0_kernel instantiations not found in the library"
+    for name, reg, stack in rows:
+        assert int(stack) == 0, f"{name} spills ({stack} bytes of stack)"
+        m = re.search(r"ILi(\d+)ELi\dELb([01])ELi\d", name)       # <CPL, METRIC, WIDE, VIS>
+        if m and int(m.group(1)) <= 2 and m.group(2) == "0":
+            assert int(reg) <= 64, f"{name}: {reg} registers, 32 one-warp CTAs per SM need <= 64"

@@ -126,3 +126,18 @@ def test_search_kernels_fit_their_register_budget_without_spills(zv):
         m = re.search(r"ILi(\d+)ELi\dELb([01])ELi\d", name)       # <CPL, METRIC, WIDE, VIS>
         if m and int(m.group(1)) <= 2 and m.group(2) == "0":
             assert int(reg) <= 64, f"{name}: {reg} registers, 32 one-warp CTAs per SM need <= 64"
+
+
+def test_library_sass_holds_the_blackwell_instructions_the_design_claims(zv):
+    """DESIGN.md's claims about the machine code, checked on the built library: the exact k-NN kernel issues 5th-gen
+    tensor-core MMAs on CTA pairs with TMA loads and TMEM reads (UTCHMMA.2CTA, UTMALDG.2D.2CTA, UTCBAR multicast commits,
+    LDTM), the search kernel uses packed f32x2 FMAs, warp REDUX for the pop selection and L2 prefetches."""
+    import shutil
+    import subprocess
+    from zvdb_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "LDTM.x32", "SYNCS.PHASECHK.TRANS64.TRYWAIT",
+                     "FFMA2", "REDUX", "CCTL.E.PF2"):
+        assert mnemonic in sass, f"{mnemonic} not found in libzvdb_b200.so"
+    assert "HMMA.16" not in sass and "WGMMA" not in sass     # no mma.sync / wgmma fallback kernels

@@ -161,3 +161,22 @@ class PyHNSW:
             if layer < len(c):
                 adj[i, : len(c[layer])] = c[layer]
         return adj
+
+    def descend(self, query):
+        """K2 (extension): insert's greedy walk (hnsw.zig:89-104) taken top down over layers max_level..1 from the
+        first node that reached max_level -> (node, distance, evaluations)."""
+        q = np.asarray(query, F)
+        levels = [len(c) - 1 for c in self.conn]
+        ep = levels.index(max(levels))
+        curr, ev = distance(q, self.points[ep]), 1
+        for layer in range(max(levels), 0, -1):
+            changed = True
+            while changed:
+                changed = False
+                cur_conn = self.conn[ep]
+                if layer < len(cur_conn):
+                    for nb in list(cur_conn[layer]):
+                        d = distance(q, self.points[nb]); ev += 1
+                        if d < curr:
+                            ep, curr, changed = nb, d, True
+        return ep, curr, ev

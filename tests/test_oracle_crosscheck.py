@@ -57,3 +57,21 @@ def test_c_oracle_equals_python_restatement_on_exact_ties(oracle):
             pids, pd, ppops, pevals = py.search(q, k)
             assert np.array_equal(ids, pids) and np.array_equal(d.view(np.uint32), pd.view(np.uint32))
             assert (pops, evals) == (ppops, pevals)
+
+
+def test_c_oracle_descent_equals_python_restatement(oracle):
+    rng = np.random.default_rng(11)
+    n, dim, m = 400, 8, 6
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    lv = _levels(n, rng)
+    py = PyHNSW(m)
+    for p, l in zip(X, lv):
+        py.insert(p, int(l))
+    o = oracle.OracleHNSW(m, 200)
+    o.insert_batch(X, levels=lv)
+    upper = o.export_upper()
+    assert upper[3] == py.max_level >= 2
+    for q in rng.standard_normal((60, dim)).astype(np.float32):
+        node, d, ev = oracle.descend_one(X, upper, q)
+        pnode, pd, pev = py.descend(q)
+        assert (node, ev) == (pnode, pev) and np.float32(d).view(np.uint32) == np.float32(pd).view(np.uint32)

@@ -13,12 +13,13 @@ import numpy as np
 F = np.float32
 
 
-def distance(a, b):                                            # hnsw.zig:182-192
+def distance(a, b):                                            # hnsw.zig:182-192, in the element type T of the rows
     assert len(a) == len(b), "Mismatched dimensions in distance calculation"
-    s = F(0)
+    T = a.dtype.type
+    s = T(0)
     for i in range(len(a)):
-        diff = F(a[i] - b[i])
-        s = F(s + F(diff * diff))
+        diff = T(a[i] - b[i])
+        s = T(s + T(diff * diff))
     return s
 
 
@@ -83,7 +84,8 @@ def insertion_sort(items, less):                               # std.sort.insert
 
 
 class PyHNSW:
-    def __init__(self, m):                                     # hnsw.zig:52-62
+    def __init__(self, m, dtype=F):                            # HNSW(T).init, hnsw.zig:8, :52-62
+        self.T = np.dtype(dtype).type
         self.m = m
         self.points = []
         self.conn = []                                         # conn[id][layer] = list of ids
@@ -92,7 +94,7 @@ class PyHNSW:
 
     def insert(self, point, level):                            # hnsw.zig:73-117 (level: randomLevel's draw, :172-180)
         nid = len(self.points)
-        p = np.asarray(point, F)
+        p = np.asarray(point, self.T)
         self.points.append(p)
         self.conn.append([[] for _ in range(level + 1)])
         if self.entry_point is not None:
@@ -135,7 +137,7 @@ class PyHNSW:
         self.conn[node][level] = cand[: self.m]
 
     def search(self, query, k):                                # hnsw.zig:194-236 -> (ids, distances, pops, evals)
-        q = np.asarray(query, F)
+        q = np.asarray(query, self.T)
         result, evals = [], 0
         if self.entry_point is not None:
             cands = ZigPriorityQueue()
@@ -152,7 +154,7 @@ class PyHNSW:
                         visited.add(nb)
         pops = len(result)
         insertion_sort(result, lambda a, b: distance(q, self.points[a]) < distance(q, self.points[b]))
-        return (np.array(result, np.uint32), np.array([distance(q, self.points[i]) for i in result], F), pops, evals)
+        return (np.array(result, np.uint32), np.array([distance(q, self.points[i]) for i in result], self.T), pops, evals)
 
     def layer(self, layer):
         """Padded adjacency [n, m] (0xFFFFFFFF) of one layer, like OracleHNSW.export_layer."""
@@ -165,7 +167,7 @@ class PyHNSW:
     def descend(self, query):
         """K2 (extension): insert's greedy walk (hnsw.zig:89-104) taken top down over layers max_level..1 from the
         first node that reached max_level -> (node, distance, evaluations)."""
-        q = np.asarray(query, F)
+        q = np.asarray(query, self.T)
         levels = [len(c) - 1 for c in self.conn]
         ep = levels.index(max(levels))
         curr, ev = distance(q, self.points[ep]), 1

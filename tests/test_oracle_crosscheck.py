@@ -75,3 +75,25 @@ def test_c_oracle_descent_equals_python_restatement(oracle):
         node, d, ev = oracle.descend_one(X, upper, q)
         pnode, pd, pev = py.descend(q)
         assert (node, ev) == (pnode, pev) and np.float32(d).view(np.uint32) == np.float32(pd).view(np.uint32)
+
+
+@pytest.mark.parametrize("dtype,npdt", [("f64", np.float64), ("i32", np.int32)])
+def test_c_oracle_equals_python_restatement_for_other_element_types(oracle, dtype, npdt):
+    """HNSW(f64) and HNSW(i32) (test_hnsw.zig:239-273): distances summed in T's own arithmetic."""
+    rng = np.random.default_rng(13)
+    n, dim, m = 200, 5, 4
+    X = (rng.standard_normal((n, dim)) * 3).astype(npdt) if dtype == "f64" else rng.integers(-20, 20, size=(n, dim)).astype(npdt)
+    lv = _levels(n, rng)
+    py = PyHNSW(m, npdt)
+    for p, l in zip(X, lv):
+        py.insert(p, int(l))
+    o = oracle.OracleHNSW(m, 200, dtype=dtype)
+    o.insert_batch(X, levels=lv)
+    for layer in range(py.max_level + 1):
+        assert np.array_equal(o.export_layer(layer)[0], py.layer(layer))
+    Q = (rng.standard_normal((25, dim)) * 3).astype(npdt) if dtype == "f64" else rng.integers(-20, 20, size=(25, dim)).astype(npdt)
+    for q in Q:
+        for k in (2, 30):
+            ids, d, pops, evals = o.search(q, k, counters=True)
+            pids, pd, ppops, pevals = py.search(q, k)
+            assert np.array_equal(ids, pids) and np.array_equal(d, pd) and (pops, evals) == (ppops, pevals)

@@ -97,3 +97,20 @@ def test_c_oracle_equals_python_restatement_for_other_element_types(oracle, dtyp
             ids, d, pops, evals = o.search(q, k, counters=True)
             pids, pd, ppops, pevals = py.search(q, k)
             assert np.array_equal(ids, pids) and np.array_equal(d, pd) and (pops, evals) == (ppops, pevals)
+
+
+def test_python_restatement_reproduces_the_hand_worked_heap_tie_golden():
+    """G11 (tests/golden/reference_tests.json): eight exact ties, pop order derived by hand from Zig's
+    PriorityQueue sift-down rule; the second restatement must land on the same order."""
+    import json
+    import os
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_tests.json")))
+    for name in ("G11_heap_tie_rule_k9", "G11_heap_tie_rule_k5"):
+        g = G[name]
+        py = PyHNSW(g["m"])
+        for p in g["points"]:
+            py.insert(np.asarray(p, np.float32), 0)
+        assert [[int(x) for x in row if x != 0xFFFFFFFF] for row in py.layer(0)] == g["layer0"]
+        ids, d, pops, evals = py.search(np.asarray(g["query"], np.float32), g["k"])
+        assert [int(x) for x in ids] == g["ids"] and [float(x) for x in d] == g["dist"]
+        assert (pops, evals) == (g["pops"], g["evals"])

@@ -24,7 +24,10 @@ def test_reference_golden(oracle, name, heap):
         assert got == g["layer0"]
     hm = oracle.HEAP_ZIG if heap == "zig" else oracle.HEAP_DET
     ids, d, pops, evals = ix.search(g["query"], g["k"], heap_mode=hm, counters=True)
-    assert [int(x) for x in ids] == g["ids"]
+    # exact ties: 'ids' is the Zig heap's pop order, 'ids_det' the (distance, id) order (see G11's derivation)
+    assert [int(x) for x in ids] == (g.get("ids_det", g["ids"]) if heap == "det" else g["ids"])
+    if "ids_if_siftdown_stopped_on_ties" in g:      # the case really distinguishes the sift-down tie rules
+        assert len({tuple(g["ids"]), tuple(g["ids_det"]), tuple(g["ids_if_siftdown_stopped_on_ties"])}) == 3
     if g["dtype"] == "f64":
         np.testing.assert_allclose(d, g["dist"], rtol=g.get("rtol", 0))
     else:

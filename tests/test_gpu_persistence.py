@@ -81,3 +81,69 @@ def test_load_rejects_bad_files(zv, tmp_path):
     b.load(path + ".empty")
     assert b.count() == 0 and b.search([0.0] * 16, 3) == []
     a.deinit(); b.deinit(); e.deinit()
+
+
+def test_handle_reused_with_a_larger_dim(zv, oracle, tmp_path):
+    """A handle whose device buffers were sized for 32-d rows is given 128-d rows by load_graph, by
+    build_from_candidates and by load: the device copy must be re-sized for the new row pitch (capacity is
+    rows x pitch, not rows), and results must equal a fresh index's and the oracle's."""
+    small, big = _gauss(1000, 32, 41), _gauss(900, 128, 42)
+    Q = _gauss(64, 128, 43)
+    fresh = zv.HNSW(8, 200)
+    fresh.insert_batch(big)
+    adj, _ = fresh.export_layer(0)
+    want = fresh.search_batch(Q, 5, 40, counters=True)
+    ref = oracle.search_graph(big, adj, Q, 40, 5, dist_mode=oracle.DIST_TREE, heap_mode=oracle.HEAP_DET)
+    assert np.array_equal(want[0], ref["ids"].astype(np.uint64))
+    path = os.path.join(tmp_path, "big.zvdb")
+    fresh.save(path)
+
+    def used_handle():
+        h = zv.HNSW(8, 200)
+        h.insert_batch(small)
+        assert np.all(h.search_batch(small[:16], 3, 12)[2] == 3)     # device buffers now exist, 32 floats per row
+        return h
+
+    h = used_handle()
+    h.load_padded_graph(big, adj, entry=0)
+    assert h.dim == 128 and h.count() == 900
+    got = h.search_batch(Q, 5, 40, counters=True)
+    assert all(np.array_equal(a, b) for a, b in zip(want, got))
+    assert np.array_equal(h.bruteforce_knn(Q[:8], 5)[0], fresh.bruteforce_knn(Q[:8], 5)[0])
+    h.deinit()
+
+    h = used_handle()
+    h.load(path)
+    got = h.search_batch(Q, 5, 40, counters=True)
+    assert all(np.array_equal(a, b) for a, b in zip(want, got))
+    h.deinit()
+
+    h = used_handle()
+    nn, _ = oracle.bruteforce(big, big, 24)
+    h.build_from_candidates(big, nn.astype(np.uint32))
+    g2 = zv.HNSW(8, 200)
+    g2.build_from_candidates(big, nn.astype(np.uint32))
+    assert np.array_equal(h.export_layer(0)[0], g2.export_layer(0)[0])
+    assert all(np.array_equal(a, b) for a, b in zip(h.search_batch(Q, 5, 40), g2.search_batch(Q, 5, 40)))
+    # and back to a smaller dim on the same handle
+    h.load_padded_graph(small, np.full((1000, 8), 0xFFFFFFFF, np.uint32), entry=0)
+    assert h.dim == 32 and np.all(h.search_batch(small[:4], 3, 3)[2] == 1)
+    h.deinit(); g2.deinit(); fresh.deinit()
+
+
+def test_wrapper_refuses_an_index_of_another_element_type(zv, tmp_path):
+    """HNSW(T) wrappers are typed at construction: loading a file of another T, or a (float32) graph into an
+    HNSW(f64), raises instead of reading rows with the wrong element size."""
+    a = zv.HNSW(8, 200, dtype=np.float64)
+    a.insert_batch(np.random.default_rng(44).standard_normal((200, 16)))
+    path = os.path.join(tmp_path, "f64.zvdb")
+    a.save(path)
+    b = zv.HNSW(8, 200)                       # an f32 wrapper
+    with pytest.raises(TypeError):
+        b.load(path)
+    c = zv.HNSW(8, 200, dtype=np.float64)
+    c.load(path)
+    assert np.array_equal(c.point(7), a.point(7))
+    with pytest.raises(TypeError):
+        c.load_padded_graph(_gauss(10, 16, 45), np.full((10, 8), 0xFFFFFFFF, np.uint32))
+    a.deinit(); b.deinit(); c.deinit()

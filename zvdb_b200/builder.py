@@ -55,7 +55,7 @@ def build_quality_graph_incremental(h, X: np.ndarray, m: int, K: int = 64, seed_
     `refine_rounds` passes follow: EVERY row is searched on the finished graph and the graph is rebuilt from those
     candidates (one batched search of n queries + one builder pass per round). With `join` = J > 0 a refinement round
     also offers every row the neighbour lists of its first J neighbours (the local join of NN-descent), J * m extra
-    candidates per row (K + J * m <= 128).
+    candidates per row (K + m + J * m <= 128).
     Cost: O(n log n) row evaluations in searches + (2 + refine_rounds) builder passes over n. Returns build statistics."""
     import time
     import torch
@@ -67,8 +67,12 @@ def build_quality_graph_incremental(h, X: np.ndarray, m: int, K: int = 64, seed_
     stream = torch.cuda.current_stream(device).cuda_stream
     t0 = time.time()
     n_cur = min(n, max(int(seed_rows), K + 1))
-    join = max(0, min(int(join), (128 - K) // m)) if refine_rounds > 0 else 0
-    KT = K + join * m                                                          # candidate slots per row (row pitch of `cand`)
+    # candidate slots per row (row pitch of `cand`, <= 128): [0, K) what the search found, then -- refinement rounds only --
+    # [K, K + m) the row's current neighbours and [K + m, KT) the local join
+    keep = m if refine_rounds > 0 else 0
+    K = max(1, min(K, 128 - keep))
+    join = max(0, min(int(join), (128 - K - keep) // m)) if refine_rounds > 0 else 0
+    KT = K + keep + join * m
     cand = torch.full((n, KT), -1, dtype=torch.int32, device=device)         # 0xFFFFFFFF = padding, tolerated by the builder
     cand[:n_cur, :K] = knn_candidates_torch(X[:n_cur], K, device)
     torch.cuda.synchronize(device)
@@ -99,11 +103,11 @@ def build_quality_graph_incremental(h, X: np.ndarray, m: int, K: int = 64, seed_
             log(f"[builder] prefix {n_cur} / {n} rows linked ({time.time() - t0:.1f}s)")
     for r in range(refine_rounds):
         search_rows(0, n)
-        # keep what the row already has: its current neighbours take the first m candidate slots, the search the rest
+        # keep what the row already has: its current neighbours are offered next to (not instead of) what the search found
         adj, _ = h.export_layer(0)
         adj_t = torch.from_numpy(adj.view(np.int32)).to(device)
         del adj
-        cand[:, :m] = adj_t
+        cand[:, K:K + m] = adj_t
         for s in range(0, n, query_chunk if join else n):                     # local join: neighbours of the first J neighbours
             if not join:
                 break
@@ -111,7 +115,7 @@ def build_quality_graph_incremental(h, X: np.ndarray, m: int, K: int = 64, seed_
             nb = adj_t[s:e, :join]
             far = adj_t[nb.clamp(min=0).long()]                               # [rows, J, m]
             far[nb < 0] = -1
-            cand[s:e, K:] = far.reshape(e - s, join * m)
+            cand[s:e, K + m:] = far.reshape(e - s, join * m)
             del nb, far
         del adj_t
         torch.cuda.synchronize(device)

@@ -78,11 +78,13 @@ struct zvdb_index {
     cudaStream_t stream_in = nullptr; // owned; carries the pipeline's host-to-device copies, so chunk c+2 arrives while chunk c still runs
     cudaEvent_t in_ev[8] = {};      // chunk c of the query batch is on the device
     cudaEvent_t bitmap_ev = nullptr; // last kernel that used the shared visited bitmaps
+    cudaEvent_t bf_ev = nullptr;     // last K4 call: its per-handle scratch (operand splits, partial lists, segment table) is shared by every call
     unsigned char *h_stage = nullptr; // owned, page-locked + device-mapped: small pageable batches (the single search call) go through it
     size_t h_stage_cap = 0;
     float *d_arena = nullptr;       // [cap_rows][row_floats]
     uint32_t *d_adj = nullptr;      // [cap_rows][m]
     uint64_t cap_rows = 0, n_dev = 0;
+    uint32_t cap_row_floats = 0, cap_m = 0;   // row layout d_arena / d_adj were sized for (a load may change dim)
     DevBuf<float> q_buf, dist_buf;
     DevBuf<uint64_t> ids_buf;
     DevBuf<uint32_t> cnt_buf, pops_buf, evals_buf, scat_rows, scat_ids, bitmap_buf, vlog_buf;
@@ -111,11 +113,21 @@ struct zvdb_index {
 
 namespace zvdb {
 
+// Device arena + layer-0 table for `rows` rows of the CURRENT row layout. Capacity is (rows, row_floats, m): a handle
+// whose contents were replaced by rows of another dim (zvdb_load, zvdb_load_graph, zvdb_build_from_candidates) gets
+// fresh buffers instead of reusing ones sized for the old pitch.
 static int ensure_capacity(zvdb_index *ix, uint64_t rows) {
-    if (rows <= ix->cap_rows) return ZVDB_OK;
+    const HostGraph &g = ix->g;
+    const bool same_layout = ix->cap_row_floats == g.row_floats && ix->cap_m == g.m;
+    if (same_layout && rows <= ix->cap_rows) return ZVDB_OK;
+    if (!same_layout) {                                   // nothing on the device is reusable
+        ZV_CUDA(cudaDeviceSynchronize());
+        cudaFree(ix->d_arena); cudaFree(ix->d_adj);
+        ix->d_arena = nullptr; ix->d_adj = nullptr; ix->cap_rows = 0; ix->n_dev = 0; ix->bf_rows = 0;
+        ix->cap_row_floats = g.row_floats; ix->cap_m = g.m;
+    }
     uint64_t nc = std::max<uint64_t>(rows, std::max<uint64_t>(ix->cap_rows * 2, 1024));
     float *na = nullptr; uint32_t *nj = nullptr;
-    const HostGraph &g = ix->g;
     ZV_CUDA(cudaMalloc(&na, nc * g.row_floats * sizeof(float)));
     cudaError_t e = cudaMalloc(&nj, nc * g.m * sizeof(uint32_t));
     if (e != cudaSuccess) { cudaFree(na); ZV_CUDA(e); }
@@ -136,6 +148,8 @@ static int sync_device_locked(zvdb_index *ix) {
     if (g.n == 0) return ZVDB_OK;
     if (g.rows_uploaded == g.n && !g.adj_all_dirty && g.dirty.empty()) return ZVDB_OK;
     ZV_CUDA(cudaSetDevice(ix->device));
+    // searches enqueued earlier on caller streams may still read the tables this is about to change
+    if (ix->n_dev) ZV_CUDA(cudaDeviceSynchronize());
     int rc = ensure_capacity(ix, g.n);
     if (rc) return rc;
     for (uint64_t r = g.rows_uploaded; r < g.n;) {
@@ -610,6 +624,8 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
     if (nq > 0x7FFFFFFFull) return fail(ZVDB_ERR_UNSUPPORTED, "nq exceeds 2^31-1 queries per launch");
     if (k > 1024) return fail(ZVDB_ERR_UNSUPPORTED, "bruteforce: k > 1024");
     const uint32_t pitch = g.row_floats;
+    // the scratch below belongs to the handle, not to the call: a call on another stream starts behind the previous one
+    ZV_CUDA(cudaStreamWaitEvent(s, ix->bf_ev, 0));
     // (1) operand split of the rows (once per index state) and of this query batch
     if (ix->bf_rows != n) {
         ZV_CUDA(ix->bf_xhi.reserve(n * pitch));
@@ -726,6 +742,7 @@ static int launch_bruteforce(zvdb_index *ix, const float *d_q, uint64_t nq, uint
                                   : launch_bf_final_metric<kMetricDot>(cpl, fp, fsmem, s);
     ix->launches++;
     ZV_CUDA(e);
+    ZV_CUDA(cudaEventRecord(ix->bf_ev, s));
     return ZVDB_OK;
 }
 
@@ -768,6 +785,7 @@ int zvdb_create(zvdb_index **out, uint32_t dim, uint32_t m, uint32_t ef_construc
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream_in, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ix->in_ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->bitmap_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->bf_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete ix; ZV_CUDA(e); }
     *out = ix;
     return ZVDB_OK;
@@ -781,6 +799,7 @@ void zvdb_destroy(zvdb_index *ix) {
     if (ix->stream_in) { cudaStreamSynchronize(ix->stream_in); cudaStreamDestroy(ix->stream_in); }
     for (int i = 0; i < 8; ++i) if (ix->in_ev[i]) cudaEventDestroy(ix->in_ev[i]);
     if (ix->bitmap_ev) cudaEventDestroy(ix->bitmap_ev);
+    if (ix->bf_ev) cudaEventDestroy(ix->bf_ev);
     cudaFree(ix->d_arena); cudaFree(ix->d_adj);
     if (ix->h_stage) cudaFreeHost(ix->h_stage);
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
@@ -861,10 +880,16 @@ int zvdb_insert_batch_typed(zvdb_index *ix, const void *points, uint64_t n, uint
     return insert_locked(ix, points, n, dim, levels, dtype);
 }
 
-int zvdb_dtype(const zvdb_index *ix) { return ix ? ix->g.dtype : 0; }
+// The accessors below take the handle's mutex like every other call: insert reallocates the vectors they read
+// (the reference's tests insert from eight threads at once, test_hnsw.zig:154-209).
+#define ZV_LOCKED(cix) std::lock_guard<std::mutex> lk(const_cast<zvdb_index *>(cix)->mu)
+
+int zvdb_dtype(const zvdb_index *ix) { if (!ix) return 0; ZV_LOCKED(ix); return ix->g.dtype; }
 
 const void *zvdb_get_point_typed(const zvdb_index *ix, uint64_t id) {
-    if (!ix || id >= ix->g.n) return nullptr;
+    if (!ix) return nullptr;
+    ZV_LOCKED(ix);
+    if (id >= ix->g.n) return nullptr;
     return ix->g.typed_point(id);
 }
 
@@ -874,7 +899,10 @@ int zvdb_search_batch_typed(zvdb_index *ix, const void *queries, uint64_t nq, ui
     if (dtype < 0 || dtype > 2) return fail(ZVDB_ERR_INVALID, "search: dtype must be 0 (f32), 1 (f64) or 2 (i32)");
     if (dtype == 0) return zvdb_search_batch(ix, static_cast<const float *>(queries), nq, dim, k, ef, ids, dist, counts, nullptr, nullptr);
     if (nq && !queries) return fail(ZVDB_ERR_INVALID, "search: null buffer");
-    if (ix->g.n && dtype != ix->g.dtype) return fail(ZVDB_ERR_INVALID, "search: element type differs from the index's");
+    {
+        ZV_LOCKED(ix);
+        if (ix->g.n && dtype != ix->g.dtype) return fail(ZVDB_ERR_INVALID, "search: element type differs from the index's");
+    }
     std::vector<float> conv;
     try { conv.resize(nq * static_cast<uint64_t>(dim)); } catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "search: out of memory"); }
     to_f32(queries, conv.size(), dtype, conv.data());
@@ -889,14 +917,20 @@ int zvdb_search_typed(zvdb_index *ix, const void *query, uint32_t dim, int dtype
     return zvdb_search_batch_typed(ix, query, 1, dim, dtype, k, k, ids, dist, count);
 }
 
-uint64_t zvdb_count(const zvdb_index *ix) { return ix ? ix->g.n : 0; }
-uint32_t zvdb_dim(const zvdb_index *ix) { return ix ? ix->g.dim : 0; }
-uint32_t zvdb_max_level(const zvdb_index *ix) { return ix ? ix->g.max_level : 0; }
-int64_t zvdb_entry_point(const zvdb_index *ix) { return (ix && ix->g.has_entry) ? static_cast<int64_t>(ix->g.entry) : -1; }
+uint64_t zvdb_count(const zvdb_index *ix) { if (!ix) return 0; ZV_LOCKED(ix); return ix->g.n; }
+uint32_t zvdb_dim(const zvdb_index *ix) { if (!ix) return 0; ZV_LOCKED(ix); return ix->g.dim; }
+uint32_t zvdb_max_level(const zvdb_index *ix) { if (!ix) return 0; ZV_LOCKED(ix); return ix->g.max_level; }
+int64_t zvdb_entry_point(const zvdb_index *ix) {
+    if (!ix) return -1;
+    ZV_LOCKED(ix);
+    return ix->g.has_entry ? static_cast<int64_t>(ix->g.entry) : -1;
+}
 
 const float *zvdb_get_point(const zvdb_index *ix, uint64_t id) {
-    if (!ix || id >= ix->g.n) return nullptr;
-    return ix->g.point(id);
+    if (!ix) return nullptr;
+    ZV_LOCKED(ix);
+    if (id >= ix->g.n) return nullptr;
+    return ix->g.point(id);   // rows live in chunks that never move: the pointer stays valid until destroy
 }
 
 int zvdb_get_connections(const zvdb_index *cix, uint64_t id, uint32_t layer, uint64_t *out, uint32_t cap, uint32_t *len) {
@@ -915,7 +949,9 @@ int zvdb_get_connections(const zvdb_index *cix, uint64_t id, uint32_t layer, uin
 }
 
 int32_t zvdb_node_level(const zvdb_index *ix, uint64_t id) {
-    if (!ix || id >= ix->g.n) return -1;
+    if (!ix) return -1;
+    ZV_LOCKED(ix);
+    if (id >= ix->g.n) return -1;
     return ix->g.level[id];
 }
 
@@ -1168,7 +1204,11 @@ int zvdb_set_descent(zvdb_index *ix, int on) {
     return ZVDB_OK;
 }
 
-int64_t zvdb_descent_start(const zvdb_index *ix) { return (ix && ix->g.has_entry) ? static_cast<int64_t>(ix->g.top_node) : -1; }
+int64_t zvdb_descent_start(const zvdb_index *ix) {
+    if (!ix) return -1;
+    ZV_LOCKED(ix);
+    return ix->g.has_entry ? static_cast<int64_t>(ix->g.top_node) : -1;
+}
 
 int zvdb_load_upper_layers(zvdb_index *ix, const uint8_t *levels, const uint32_t *upper_adj, uint64_t n_lists, uint64_t start) {
     if (!ix || !levels || (n_lists && !upper_adj)) return fail(ZVDB_ERR_INVALID, "null argument");
@@ -1223,17 +1263,9 @@ int zvdb_export_upper_layers(const zvdb_index *cix, uint8_t *levels, uint32_t *u
     return ZVDB_OK;
 }
 
-int zvdb_build_from_candidates(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, const uint32_t *cand,
-                               uint32_t K, int cand_on_device) {
-    if (!ix || (n && (!points || !cand))) return fail(ZVDB_ERR_INVALID, "null argument");
-    if (K == 0 || K > kBuildBuf) return fail(ZVDB_ERR_UNSUPPORTED, "build: K must be in 1..128");
-    std::lock_guard<std::mutex> lk(ix->mu);
+static int build_from_candidates_locked(zvdb_index *ix, uint64_t n, const uint32_t *cand, uint32_t K, int cand_on_device) {
     HostGraph &g = ix->g;
-    if (g.m > 64) return fail(ZVDB_ERR_UNSUPPORTED, "build: m must be <= 64");
-    int rc = set_points_locked(ix, points, n, dim, 0);   // entry point = node 0, as in the reference
-    if (rc || n == 0) return rc;
-    g.adj_all_dirty = false;                             // the table is produced on the device
-    rc = ensure_capacity(ix, n);
+    int rc = ensure_capacity(ix, n);
     if (rc) return rc;
     cudaStream_t s = ix->stream;
     for (uint64_t r = 0; r < n;) {                       // arena rows up
@@ -1244,18 +1276,20 @@ int zvdb_build_from_candidates(zvdb_index *ix, const float *points, uint64_t n, 
     }
     DevBuf<uint32_t> d_cand, d_fw, d_indeg, d_rev;
     DevBuf<uint64_t> d_off;
+    struct Cleanup {                                     // every exit frees the build scratch
+        DevBuf<uint32_t> &a, &b, &c, &d; DevBuf<uint64_t> &e;
+        ~Cleanup() { a.free_(); b.free_(); c.free_(); d.free_(); e.free_(); }
+    } cleanup{d_cand, d_fw, d_indeg, d_rev, d_off};
     const uint32_t *cand_dev = cand;
     if (!cand_on_device) {
         ZV_CUDA(d_cand.reserve(n * K));
         ZV_CUDA(cudaMemcpyAsync(d_cand.p, cand, n * K * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         cand_dev = d_cand.p;
     }
-    auto cleanup = [&]() { d_cand.free_(); d_fw.free_(); d_indeg.free_(); d_rev.free_(); d_off.free_(); };
-#define ZV_B(expr) do { cudaError_t e2__ = (expr); if (e2__ != cudaSuccess) { cleanup(); ZV_CUDA(e2__); } } while (0)
-    ZV_B(d_fw.reserve(n * g.m));
-    ZV_B(d_indeg.reserve(2 * n));
-    ZV_B(d_off.reserve(n + 1));
-    ZV_B(cudaMemsetAsync(d_indeg.p, 0, 2 * n * sizeof(uint32_t), s));
+    ZV_CUDA(d_fw.reserve(n * g.m));
+    ZV_CUDA(d_indeg.reserve(2 * n));
+    ZV_CUDA(d_off.reserve(n + 1));
+    ZV_CUDA(cudaMemsetAsync(d_indeg.p, 0, 2 * n * sizeof(uint32_t), s));
     BuildParams bp{};
     bp.arena = reinterpret_cast<const float4 *>(ix->d_arena);
     bp.row_chunks = g.row_floats / 4; bp.n = static_cast<uint32_t>(n); bp.m = g.m;
@@ -1263,26 +1297,48 @@ int zvdb_build_from_candidates(zvdb_index *ix, const float *points, uint64_t n, 
     const uint32_t cpl_raw = (bp.row_chunks + 31) / 32;
     const int cpl = cpl_raw <= 1 ? 1 : cpl_raw <= 2 ? 2 : cpl_raw <= 4 ? 4 : cpl_raw <= 6 ? 6 : 8;
     launch_build(g.metric, cpl, 1, bp, s); ix->launches++;
-    ZV_B(cudaGetLastError());
+    ZV_CUDA(cudaGetLastError());
     const uint64_t total = n * g.m;
     const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((total + 255) / 256, 148ull * 16));
     count_reverse_kernel<<<blocks, 256, 0, s>>>(d_fw.p, total, d_indeg.p); ix->launches++;
-    std::vector<uint32_t> indeg(n);
-    ZV_B(cudaMemcpyAsync(indeg.data(), d_indeg.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    ZV_B(cudaStreamSynchronize(s));
-    std::vector<uint64_t> off(n + 1);
+    std::vector<uint32_t> indeg;
+    std::vector<uint64_t> off;
+    try { indeg.resize(n); off.resize(n + 1); }
+    catch (const std::bad_alloc &) { return fail(ZVDB_ERR_OUT_OF_MEMORY, "build: out of memory"); }
+    ZV_CUDA(cudaMemcpyAsync(indeg.data(), d_indeg.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ZV_CUDA(cudaStreamSynchronize(s));
     off[0] = 0;
     for (uint64_t i = 0; i < n; ++i) off[i + 1] = off[i] + indeg[i];
-    ZV_B(d_rev.reserve(std::max<uint64_t>(off[n], 1)));
-    ZV_B(cudaMemcpyAsync(d_off.p, off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    ZV_CUDA(d_rev.reserve(std::max<uint64_t>(off[n], 1)));
+    ZV_CUDA(cudaMemcpyAsync(d_off.p, off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     fill_reverse_kernel<<<blocks, 256, 0, s>>>(d_fw.p, total, g.m, d_off.p, d_indeg.p + n, d_rev.p); ix->launches++;
     bp.rev_off = d_off.p; bp.rev = d_rev.p;
     launch_build(g.metric, cpl, 3, bp, s); ix->launches++;
-    ZV_B(cudaGetLastError());
-    ZV_B(cudaMemcpyAsync(g.adj0.data(), ix->d_adj, n * g.m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    ZV_B(cudaStreamSynchronize(s));
-#undef ZV_B
-    cleanup();
+    ZV_CUDA(cudaGetLastError());
+    ZV_CUDA(cudaMemcpyAsync(g.adj0.data(), ix->d_adj, n * g.m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ZV_CUDA(cudaStreamSynchronize(s));
+    return ZVDB_OK;
+}
+
+int zvdb_build_from_candidates(zvdb_index *ix, const float *points, uint64_t n, uint32_t dim, const uint32_t *cand,
+                               uint32_t K, int cand_on_device) {
+    if (!ix || (n && (!points || !cand))) return fail(ZVDB_ERR_INVALID, "null argument");
+    if (K == 0 || K > kBuildBuf) return fail(ZVDB_ERR_UNSUPPORTED, "build: K must be in 1..128");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    HostGraph &g = ix->g;
+    if (g.m > 64) return fail(ZVDB_ERR_UNSUPPORTED, "build: m must be <= 64");
+    int rc = set_points_locked(ix, points, n, dim, 0);   // entry point = node 0, as in the reference
+    if (rc || n == 0) return rc;
+    rc = build_from_candidates_locked(ix, n, cand, K, cand_on_device);
+    if (rc) {
+        // A failed build must not leave n searchable rows without an adjacency table on either side: the index
+        // becomes empty (the error string of the failing step is kept).
+        const std::string why = g_last_error;
+        g.reset_nodes();
+        ix->n_dev = 0; ix->bf_rows = 0;
+        return fail(rc, why);
+    }
+    // the table was produced on the device and copied back: both sides are current
     g.rows_uploaded = n; g.dirty.clear(); g.adj_all_dirty = false;
     ix->n_dev = n;
     return ZVDB_OK;

@@ -203,18 +203,23 @@ struct HostGraph {
             }
             std::memcpy(const_cast<void *>(typed_point(id)), typed, static_cast<size_t>(dim) * elem_size());
         }
+        const size_t upper_before = upper.size();
         try {
             adj0.resize((id + 1) * m, kInvalidId);
             level.push_back(static_cast<uint8_t>(lv));
             if (lv > 0) {
-                ++upper_version;
                 upper_off.push_back(upper.size());
                 upper.resize(upper.size() + lv, 0u);
                 upper.resize(upper.size() + static_cast<size_t>(lv) * m, kInvalidId);
+                ++upper_version;
             } else {
                 upper_off.push_back(~0ull);
             }
-        } catch (const std::bad_alloc &) { return 1; }
+        } catch (const std::bad_alloc &) {
+            // roll the per-node arrays back to n entries (shrinking never throws): a failed insert changes nothing
+            adj0.resize(id * m); level.resize(id); upper_off.resize(id); upper.resize(upper_before);
+            return 1;
+        }
         float *row = point_mut(id);
         std::memcpy(row, pt, dim * sizeof(float));                               // owned copy, :24-26
         if (metric == 1) {                                                       // cosine: normalise once

@@ -170,8 +170,23 @@ class HNSW:
         L.check(L.lib().zvdb_insert_batch(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.shape[0], p.shape[1],
                                           lv.ctypes.data_as(C.POINTER(C.c_int32)) if lv is not None else None))
 
+    def _require_f32(self, what: str) -> None:
+        """load_graph / build_from_candidates produce an f32 index: HNSW(f64) / HNSW(i32) wrappers refuse them
+        (they would read f32 rows as T afterwards)."""
+        if self._dt:
+            raise TypeError(f"{what}: graphs are loaded and built as float32 rows; this wrapper is HNSW({self.dtype.name})")
+
+    def _check_dtype(self, what: str) -> None:
+        """The library adopts the element type of what it was given (zvdb_load: the file's); it must be this wrapper's T."""
+        got = int(L.lib().zvdb_dtype(self._h))
+        if got != self._dt and self.count() > 0:
+            names = {v: k.name for k, v in self._DTYPES.items()}
+            raise TypeError(f"{what}: the index now holds {names.get(got, got)} rows, this wrapper is HNSW({self.dtype.name}); "
+                            "open it with the matching dtype")
+
     def load_graph(self, points, offsets, nbrs, entry: int = 0) -> None:
         """Replace the index by an external graph in CSR form (layer 0 only)."""
+        self._require_f32("load_graph")
         p = np.ascontiguousarray(points, np.float32)
         off = np.ascontiguousarray(offsets, np.uint64)
         nb = np.ascontiguousarray(nbrs, np.uint32)
@@ -191,6 +206,7 @@ class HNSW:
     def build_from_candidates(self, points, cand=None, K: int = 0, cand_device_ptr: int = 0) -> None:
         """Replace the index by a graph built on the GPU from candidate lists (builder.cuh).
         `cand`: host array [n, K] of uint32 ids, or pass cand_device_ptr + K for a device array."""
+        self._require_f32("build_from_candidates")
         p = np.ascontiguousarray(points, np.float32)
         if cand_device_ptr:
             L.check(L.lib().zvdb_build_from_candidates(self._h, p.ctypes.data_as(C.POINTER(C.c_float)), p.shape[0],
@@ -234,6 +250,7 @@ class HNSW:
     def load(self, path: str) -> None:
         """Replace this index's contents by the file's (same m and metric required)."""
         L.check(L.lib().zvdb_load(self._h, str(path).encode()))
+        self._check_dtype("load")
 
     # -- search (hnsw.zig:194) -------------------------------------------------------------------
     def search(self, query: Sequence[float], k: int) -> list:

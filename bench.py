@@ -76,11 +76,12 @@ def parse_args():
                    help="reference = the reference's insert; quality = GPU builder on exact (GEMM) candidates, O(n^2); "
                         "incremental = GPU builder on candidates from the index's own search (scales to C4 shards)")
     p.add_argument("--sweep", action="store_true", help="also report the ef sweep 32..512 (untimed extra passes)")
-    p.add_argument("--variant", type=int, default=0, help="search kernel variant: 0 auto, 1 narrow, 2 wide")
+    p.add_argument("--variant", type=int, default=0, help="zvdb_set_kernel_variant bits (0 = automatic; e.g. 8 = global bitmap, 12 = global hash visited set)")
     p.add_argument("--cpu-sample", type=int, default=0, help="--impl reference: queries per step (0 = the whole batch, like a GPU step)")
     p.add_argument("--cpu-seconds", type=float, default=10.0, help="cpu_baseline leg: keep passing over the query batches for about this long")
-    p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                   help="N>1: fused peer-store exchange inside the search kernel, or one NCCL all-gather")
+    p.add_argument("--exchange", default="p2p", choices=["p2p", "p2p3", "nccl"],
+                   help="N>1: p2p = ONE launch per step (search + peer stores + per-query flags + merge one wave behind), "
+                        "p2p3 = round 1's three launches (search with peer stores, flag kernel, merge kernel), nccl = search, one NCCL all-gather, merge kernel")
     p.add_argument("--descent", action="store_true", help="K2: walk the upper layers before the layer-0 search (extension; "
                                                           "needs upper layers: the reference graph has them)")
     p.add_argument("--shard-gen", action="store_true", help="generate each rank's rows on that rank only (large --n, e.g. C4); "
@@ -443,7 +444,9 @@ def run_ours(args):
         m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         m_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
         m_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
-        if args.exchange == "p2p":
+        if args.exchange in ("p2p", "p2p3"):
+            if args.exchange == "p2p3":
+                h.set_kernel_variant(args.variant | 0x1000)
             backend.open_exchange(nq, k, None)
         else:
             blk = torch.empty(block_bytes(nq, k), dtype=torch.uint8, device=dev)
@@ -466,9 +469,9 @@ def run_ours(args):
             h.search_batch_device(q.data_ptr(), nq, k, e, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(),
                                   d_pops.data_ptr(), d_evals.data_ptr(), stream=stream)
             launches[0] += 1
-        elif args.exchange == "p2p":
-            backend.search_exchange(q, nq, k, e, out=(o_ids, o_dist, o_cnt))      # search(+peer stores), signal, merge
-            launches[0] += 3
+        elif args.exchange in ("p2p", "p2p3"):
+            backend.search_exchange(q, nq, k, e, out=(o_ids, o_dist, o_cnt))      # one fused launch (p2p3: search, signal, merge)
+            launches[0] += 1 if args.exchange == "p2p" else 3
         else:
             zvdb_b200._lib.check(zvdb_b200.lib().zvdb_search_batch_packed_device(h._h, q.data_ptr(), nq, k, e, blk.data_ptr(),
                                                                                  world, rank, stream))
@@ -650,9 +653,9 @@ def run_ours(args):
     e2e = {"value": nq * args.steps / float(e_dt.item()), "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4 * copies,
            "d2h_bytes_per_step": (nq * k * 12 + nq * 4) * copies,
            "api": "zvdb_search_batch (page-locked host pointers; the kernel reads the batch from and writes the results to host memory)" if world == 1 else
-                  (f"per rank: 1/{world} of the page-locked batch H2D + all-gather over NVLink + zvdb_search_batch_{'exchange' if args.exchange == 'p2p' else 'packed_device + all_gather + merge'} + 1/{world} of the merged top-k D2H"
+                  (f"per rank: 1/{world} of the page-locked batch H2D + all-gather over NVLink + zvdb_search_batch_{'exchange' if args.exchange != 'nccl' else 'packed_device + all_gather + merge'} + 1/{world} of the merged top-k D2H"
                    if args.e2e_input == "sliced" else
-                   f"per rank: zvdb_search_batch_{'exchange' if args.exchange == 'p2p' else 'packed_device + all_gather + merge'} on page-locked host query/result buffers (read and written by the kernels over PCIe)")}
+                   f"per rank: zvdb_search_batch_{'exchange' if args.exchange != 'nccl' else 'packed_device + all_gather + merge'} on page-locked host query/result buffers (read and written by the kernels over PCIe)")}
     if staged_qps is not None:
         e2e["staged_copies_qps"] = staged_qps
     if world > 1:

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""K1 tuning sweep on one B200: time every kernel variant (visited set x load width) per ef on both
+"""K1 tuning sweep on one B200: time every visited-set variant (shared-memory hash, global bitmap, global hash) per ef on both
 graphs. Prints one JSON line per (graph, ef, variant). Not part of the product or the tests."""
 import json, sys, time
 import numpy as np, torch
@@ -20,11 +20,11 @@ for graph in ("reference", "quality"):
     h = zvdb_b200.HNSW(m, 200)
     t0 = time.time()
     if graph == "reference": h.insert_batch(X)
-    else: builder.build_quality_graph(h, X, m)
+    else: builder.build_quality_graph_incremental(h, X, m)
     h.sync_device()
     print(f"# {graph} built in {time.time()-t0:.1f}s", flush=True)
     for ef in (16, 32, 64, 128, 256, 512, 1024):
-        for variant in (0b0101, 0b0110, 0b1001, 0b1010):
+        for variant in (0b0100, 0b1000, 0b1100):
             h.set_kernel_variant(variant)
             try:
                 for _ in range(2):
@@ -36,8 +36,7 @@ for graph in ("reference", "quality"):
                     h.search_batch_device(dq.data_ptr(), nq, k, ef, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(), stream=stream)
                 b.record(); torch.cuda.synchronize()
                 ms = a.elapsed_time(b) / 3
-                print(json.dumps({"graph": graph, "m": m, "ef": ef, "vis": "hash" if (variant >> 2) == 1 else "bitmap",
-                                  "width": "narrow" if (variant & 3) == 1 else "wide", "ms": round(ms, 4), "qps": round(nq / ms * 1e3)}), flush=True)
+                print(json.dumps({"graph": graph, "m": m, "ef": ef, "vis": {1: "smem_hash", 2: "global_bitmap", 3: "global_hash"}[variant >> 2], "ms": round(ms, 4), "qps": round(nq / ms * 1e3)}), flush=True)
             except zvdb_b200.ZvdbError as e:
                 print(json.dumps({"graph": graph, "ef": ef, "variant": variant, "error": str(e)[:80]}), flush=True)
     h.deinit()

@@ -141,7 +141,7 @@ def test_kernel_variants_agree_under_metric(zv, oracle, name):
     h.insert_batch(X)
     Q = _gauss(200, 128, 144)
     base = h.search_batch(Q, 10, 96, counters=True)
-    for variant in (0b0101, 0b0110, 0b1001, 0b1010):
+    for variant in (0b0100, 0b1000, 0b1100):        # shared-memory hash, global bitmap, global hash
         h.set_kernel_variant(variant)
         got = h.search_batch(Q, 10, 96, counters=True)
         for a, b in zip(base, got):

@@ -263,8 +263,10 @@ def test_search_bit_exact_vs_oracle(zv, oracle, n, dim, m, k, ef):
     h.deinit()
 
 
-@pytest.mark.parametrize("warps", [0b0101, 0b0110, 0b1001, 0b1010,     # {smem hash, global bitmap} x {narrow, wide}
-                                   0x105, 0x305, 0x405, 0x109, 0x209, 0x309, 0x409])   # x L2 prefetch {off, rows, adjacency, both}
+@pytest.mark.parametrize("warps", [0b0100, 0b1000, 0b1100,             # visited set: shared-memory hash, global bitmap, global hash
+                                   0b0101, 0b1010,                     # (bits 0-1, round 1's load widths: accepted, ignored)
+                                   0x104, 0x304, 0x404,                # x L2 prefetch {off, rows, adjacency, both}
+                                   0x108, 0x208, 0x308, 0x408, 0x10C, 0x20C, 0x30C, 0x40C])
 def test_kernel_variant_does_not_change_results(zv, oracle, warps):
     X, h, adj = _build_pair(zv, oracle, 6000, 128, 16, 43)
     Q = _gauss(300, 128, 44)
@@ -273,6 +275,35 @@ def test_kernel_variant_does_not_change_results(zv, oracle, warps):
     got = h.search_batch(Q, 10, 96, counters=True)
     for a, b in zip(base, got):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    h.deinit()
+
+
+@pytest.mark.parametrize("vis", [0b1000, 0b1100])                      # global bitmap, global hash
+@pytest.mark.parametrize("n,dim,m,k,ef", [
+    (20000, 128, 16, 10, 512),    # the large-ef path of C2: persistent CTAs, popped keys in global scratch
+    (3000, 128, 16, 10, 700),     # ef * m > n: the table is sized by n, nearly every row is visited
+    (6000, 64, 40, 10, 200),      # m > 32: two adjacency passes per pop
+    (300, 16, 4, 5, 300),         # tiny index, ef = n: the search runs dry
+])
+def test_global_visited_modes_bit_exact_vs_oracle(zv, oracle, vis, n, dim, m, k, ef):
+    """The two global-memory visited sets (the per-CTA hash table sized by ef*m that round 2 made the default beyond
+    ef = 64, and round 1's n-bit bitmap) against the oracle, with many more queries than resident CTAs' worth of
+    table reuse would need to expose a table that is not left clean."""
+    X, h, adj = _build_pair(zv, oracle, n, dim, m, 45)
+    h.set_kernel_variant(vis)
+    Q = _gauss(700, dim, 46)
+    for rep in range(2):                                # second pass reuses every CTA's table
+        ids, dist, counts, pops, evals = h.search_batch(Q, k, ef, counters=True)
+        ref = oracle.search_graph(X, adj, Q, ef, k, dist_mode=oracle.DIST_TREE, heap_mode=oracle.HEAP_DET)
+        assert np.array_equal(counts, ref["counts"]) and np.array_equal(pops, ref["pops"]) and np.array_equal(evals, ref["evals"])
+        mask = np.arange(k)[None, :] < counts[:, None]
+        assert np.array_equal(ids[mask], ref["ids"].astype(np.uint64)[mask])
+        assert np.array_equal(dist.view(np.uint32)[mask], ref["dist"].view(np.uint32)[mask])
+    # a different ef on the same handle: another table pitch over the same scratch
+    ids, dist, counts = h.search_batch(Q, k, max(k, ef // 3))
+    ref = oracle.search_graph(X, adj, Q, max(k, ef // 3), k, dist_mode=oracle.DIST_TREE, heap_mode=oracle.HEAP_DET)
+    mask = np.arange(k)[None, :] < counts[:, None]
+    assert np.array_equal(ids[mask], ref["ids"].astype(np.uint64)[mask])
     h.deinit()
 
 

@@ -31,13 +31,14 @@ def _sharded_oracle(O, X, Q, world, m, k, e):
     return O.merge_topk(np.stack(D), np.stack(I), np.stack(Cn))
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("exchange", ["p2p", "p2p3", "nccl"])
 def test_single_rank_sharded_equals_plain_search(zv, oracle, exchange):
     from zvdb_b200.sharded import ShardedHNSW
     X, Q = _gauss(6000, 64, 101), _gauss(200, 64, 102)
     sh = ShardedHNSW(16, 200, rank=0, world=1, device=0, exchange=exchange)
+    assert np.all(sh.search_batch(Q[:7], 5, 9)[2] == 0)      # an empty shard publishes zero results per query
     sh.insert_batch(X[:11]); sh.insert_batch(X[11:])
-    for k, ef in ((10, 10), (10, 64), (100, 128)):
+    for k, ef in ((10, 10), (10, 64), (100, 128), (10, 300)):   # (10, 300): persistent CTAs merge one iteration behind
         ids, dist, counts = sh.search_batch(Q, k, ef)
         i0, d0, c0 = sh.index.search_batch(Q, k, ef)
         assert np.array_equal(counts, c0) and np.array_equal(ids, i0)
@@ -48,6 +49,27 @@ def test_single_rank_sharded_equals_plain_search(zv, oracle, exchange):
     for _ in range(5):                      # repeated calls alternate the two halves of the gather buffer
         ids2, _, _ = sh.search_batch(Q, 10, 64)
     assert np.array_equal(ids2, sh.index.search_batch(Q, 10, 64)[0])
+    sh.deinit()
+
+
+@pytest.mark.parametrize("k,ef", [(10, 16), (10, 300), (100, 100)])
+def test_fused_step_with_more_queries_than_resident_ctas(zv, k, ef):
+    """The one-launch sharded step merges one wave behind the search: with 12 000 queries every kind of CTA occurs --
+    search-only (first wave), search + merge, merge-only (the trailing wave of one-CTA-per-query grids) and, at
+    ef = 300, persistent CTAs that merge what they searched one iteration ago. Result = the plain search, bit for bit,
+    call after call (the gather buffer alternates its two halves, flags carry the epoch)."""
+    from zvdb_b200.sharded import ShardedHNSW
+    X, Q = _gauss(5000, 32, 111), _gauss(12000, 32, 112)
+    sh = ShardedHNSW(16, 200, rank=0, world=1, device=0, exchange="p2p")
+    sh.insert_batch(X)
+    want = sh.index.search_batch(Q, k, ef)
+    for rep in range(3):
+        got = sh.search_batch(Q, k, ef)
+        for a, b in zip(want, got):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), rep
+    got = sh.search_batch(Q[:100], k, ef)                   # a smaller batch on the same exchange object
+    for a, b in zip(want, got):
+        assert np.array_equal(a[:100].view(np.uint8), b.view(np.uint8))
     sh.deinit()
 
 
@@ -85,7 +107,7 @@ def _worker(rank, world, port, outdir, n, dim, m, nq, k, ef):
                             device_id=torch.device("cuda", rank))
     X, Q = _gauss(n, dim, 104), _gauss(nq, dim, 105)
     out = {}
-    for exchange in ("p2p", "nccl"):
+    for exchange in ("p2p", "p2p3", "nccl"):
         sh = ShardedHNSW(m, 200, device=rank, exchange=exchange)
         sh.insert_batch(X)
         for rep in range(3):
@@ -113,7 +135,7 @@ def test_two_gpu_sharded_search_matches_the_sharded_oracle(zv, oracle):
     X, Q = _gauss(n, dim, 104), _gauss(nq, dim, 105)
     d, i, c = _sharded_oracle(oracle, X, Q, world, m, k, per_shard_ef(ef, k, world))
     for r in range(world):
-        for e in ("p2p", "nccl"):
+        for e in ("p2p", "p2p3", "nccl"):
             assert np.array_equal(got[r][f"{e}_counts"], c), (r, e)
             assert np.array_equal(got[r][f"{e}_ids"], i), (r, e)
             assert np.array_equal(got[r][f"{e}_dist"].view(np.uint32), d.view(np.uint32)), (r, e)

@@ -88,7 +88,8 @@ struct zvdb_index {
     DevBuf<float> q_buf, dist_buf;
     DevBuf<uint64_t> ids_buf;
     DevBuf<uint32_t> cnt_buf, pops_buf, evals_buf, scat_rows, scat_ids, bitmap_buf, vlog_buf;
-    DevBuf<uint64_t> res_buf;       // bitmap mode: per-CTA popped-key lists
+    DevBuf<uint64_t> res_buf;       // global visited modes: per-CTA popped-key lists
+    DevBuf<uint32_t> gtable_buf;    // global-hash mode: one open-addressing table per resident CTA, all kInvalidId between launches
     // K4 (brute force): TF32 hi/lo split of the arena + squared row norms, rebuilt when the rows change
     DevBuf<float> bf_xhi, bf_xlo, bf_xnorm, bf_qhi, bf_qlo;
     DevBuf<uint64_t> bf_part, bf_glists;
@@ -101,8 +102,8 @@ struct zvdb_index {
     DevBuf<uint4> seeds_buf;        // per-query output of descend_kernel
     uint64_t upper_uploaded = ~0ull;
     bool descent = false;           // off = the reference's search (entry_point, layer 0 only)
-    uint32_t variant = 0;           // 0 automatic, 1 narrow, 2 wide (tuning/testing)
-    uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap
+    uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap, 3 global hash
+    bool legacy_exchange = false;   // sharded step as three launches (search with peer stores, flag kernel, merge kernel) instead of one
     bool stage_host_buffers = false; // zvdb_search_batch: always copy through device staging buffers (variant bit 11; A/B against zero-copy)
     uint32_t prefetch_mode = 0;     // K1 L2 prefetch: 0 automatic, else 1 + bits (bit 0 rows of a pop's later batches, bit 1 adjacency rows of evaluated neighbours)
     uint32_t bf_mode = 0;           // K4: 0 automatic (CTA pairs), 1 single CTAs, 2 CTA pairs
@@ -214,9 +215,9 @@ static int sync_upper_locked(zvdb_index *ix) {
 
 // ---- K1 launch ------------------------------------------------------------------------------
 
-template <int CPL, int METRIC, bool WIDE, int VIS>
+template <int CPL, int METRIC, int VIS>
 static cudaError_t launch_search_inst(const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
-    auto kern = search_layer0_kernel<CPL, METRIC, WIDE, VIS>;
+    auto kern = search_layer0_kernel<CPL, METRIC, VIS>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
@@ -225,24 +226,24 @@ static cudaError_t launch_search_inst(const SearchParams &p, unsigned grid, size
     return cudaGetLastError();
 }
 
-template <int METRIC, bool WIDE, int VIS>
+template <int METRIC, int VIS>
 static cudaError_t launch_search_metric(int cpl, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     switch (cpl) {
-        case 1: return launch_search_inst<1, METRIC, WIDE, VIS>(p, grid, smem, s);
-        case 2: return launch_search_inst<2, METRIC, WIDE, VIS>(p, grid, smem, s);
-        case 4: return launch_search_inst<4, METRIC, WIDE, VIS>(p, grid, smem, s);
-        case 6: return launch_search_inst<6, METRIC, WIDE, VIS>(p, grid, smem, s);
-        case 8: return launch_search_inst<8, METRIC, WIDE, VIS>(p, grid, smem, s);
+        case 1: return launch_search_inst<1, METRIC, VIS>(p, grid, smem, s);
+        case 2: return launch_search_inst<2, METRIC, VIS>(p, grid, smem, s);
+        case 4: return launch_search_inst<4, METRIC, VIS>(p, grid, smem, s);
+        case 6: return launch_search_inst<6, METRIC, VIS>(p, grid, smem, s);
+        case 8: return launch_search_inst<8, METRIC, VIS>(p, grid, smem, s);
     }
     return cudaErrorInvalidValue;
 }
 
-template <bool WIDE, int VIS>
-static cudaError_t launch_search_wv(int metric, int cpl, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+template <int VIS>
+static cudaError_t launch_search_vis(int metric, int cpl, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     switch (metric) {
-        case 0: return launch_search_metric<kMetricL2, WIDE, VIS>(cpl, p, grid, smem, s);
-        case 1: return launch_search_metric<kMetricCos, WIDE, VIS>(cpl, p, grid, smem, s);
-        default: return launch_search_metric<kMetricDot, WIDE, VIS>(cpl, p, grid, smem, s);
+        case 0: return launch_search_metric<kMetricL2, VIS>(cpl, p, grid, smem, s);
+        case 1: return launch_search_metric<kMetricCos, VIS>(cpl, p, grid, smem, s);
+        default: return launch_search_metric<kMetricDot, VIS>(cpl, p, grid, smem, s);
     }
 }
 
@@ -275,17 +276,31 @@ static int plan_visited(const zvdb_index *ix, uint32_t ef) {
     const uint64_t smem_lists = (((static_cast<uint64_t>(ef) + 1) & ~1ull) + cand_cap) * 8 + kPoolCap * 8 + 32 * 4 + kPoolCap * 4 + 16;
     const uint64_t smem_hash = smem_lists + slots * 4;
     const uint64_t ctas = std::min<uint64_t>(32, (227ull * 1024) / (smem_hash + 1024));
-    int vis = (smem_hash <= ix->smem_optin && ctas >= 20) ? kVisSmemHash : kVisGlobalBitmap;
+    // On chip while that still leaves >= 20 queries per SM; beyond that the same hash table per resident CTA in
+    // global memory (sized by ef * m, so it stays in L2 however many rows the index has).
+    int vis = (smem_hash <= ix->smem_optin && ctas >= 20) ? kVisSmemHash : kVisGlobalHash;
     if (ix->visited_mode == 1) vis = kVisSmemHash;
     if (ix->visited_mode == 2) vis = kVisGlobalBitmap;
+    if (ix->visited_mode == 3) vis = kVisGlobalHash;
     return vis;
 }
+
+// The receiving side of a fused sharded step (zvdb_search_batch_exchange): see SearchParams.
+struct FusedExchange {
+    uint32_t *peer_qflags[8];
+    const uint32_t *qflags;
+    const uint8_t *gather;
+    uint64_t block_bytes;
+    uint64_t *m_ids; float *m_dist; uint32_t *m_counts;
+    uint32_t world, rank, epoch;
+};
 
 // Device buffers in, device buffers out, no synchronisation. Caller holds the lock and has synced
 // the device copy.
 static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t *d_ids,
                          float *d_dist, uint32_t *d_counts, uint32_t *d_pops, uint32_t *d_evals, uint64_t id_stride,
-                         uint64_t id_base, cudaStream_t s, uint8_t *const *peer_blocks = nullptr, uint32_t n_peers = 0) {
+                         uint64_t id_base, cudaStream_t s, uint8_t *const *peer_blocks = nullptr, uint32_t n_peers = 0,
+                         const FusedExchange *fx = nullptr) {
     const HostGraph &g = ix->g;
     if (nq == 0) return ZVDB_OK;
     if (nq > 0x7FFFFFFFull) return fail(ZVDB_ERR_UNSUPPORTED, "nq exceeds 2^31-1 queries per launch");
@@ -300,7 +315,7 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     p.row_chunks = g.row_floats / 4;
     p.m = g.m; p.n = static_cast<uint32_t>(g.n); p.entry = static_cast<uint32_t>(g.entry); p.dim = g.dim;
     p.nq = static_cast<uint32_t>(nq); p.k = k; p.ef = ef;
-    if (ix->descent && g.max_level > 0) {                 // K2: start at the top node, walk down, then the beam
+    if (ix->descent && g.max_level > 0 && g.n > 0) {      // K2: start at the top node, walk down, then the beam
         int rcu = sync_upper_locked(ix);
         if (rcu) return rcu;
         p.levels = ix->d_level.p; p.upper_base = ix->d_upper_base.p; p.upper_adj = ix->d_upper_adj.p;
@@ -315,89 +330,104 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     if (chunks_per_lane > 8) return fail(ZVDB_ERR_UNSUPPORTED, "dim > 1024 is not built into the search kernel");
     const int cpl = chunks_per_lane <= 1 ? 1 : chunks_per_lane <= 2 ? 2 : chunks_per_lane <= 4 ? 4 : chunks_per_lane <= 6 ? 6 : 8;
 
-    const uint64_t bound = std::min<uint64_t>(g.n, 1ull + static_cast<uint64_t>(ef) * g.m);   // visited-set maximum
+    const uint64_t bound = std::max<uint64_t>(1, std::min<uint64_t>(g.n, 1ull + static_cast<uint64_t>(ef) * g.m));   // visited-set maximum
     const uint64_t slots = bound + bound / 4 + 16;
+    const uint64_t hash_words = (slots + 3) & ~3ull;                   // tables are wiped 16 bytes at a time
     const uint64_t cand_cap = std::max<uint64_t>(2, next_pow2(ef));   // >= ef, even (alignment), reused by the final sort
     const uint64_t smem_lists = (((static_cast<uint64_t>(ef) + 1) & ~1ull) + cand_cap) * 8 + kPoolCap * 8 + 32 * 4 + kPoolCap * 4 + 16;
     const uint64_t smem_hash = smem_lists + slots * 4;
+    // fused exchange: the merge of world * k candidates needs its own scratch (keys + global ids) behind the search's
+    uint64_t merge_smem = 0;
+    if (fx) {
+        const uint64_t total = static_cast<uint64_t>(fx->world) * k;
+        if (total > 4096) return fail(ZVDB_ERR_UNSUPPORTED, "merge: G*k > 4096");
+        p.merge_p2 = next_pow2(static_cast<uint32_t>(total));
+        merge_smem = (static_cast<uint64_t>(p.merge_p2) + total) * 8;
+    }
     auto ctas_for = [](uint64_t smem) { return std::min<uint64_t>(32, (227ull * 1024) / (smem + 1024)); };
-    // Where the exact visited set lives. On chip while that still leaves >= 20 warps per SM; beyond
-    // that a per-CTA bitmap in global memory keeps residency up (one atomicOr per neighbour).
     const int vis = plan_visited(ix, ef);
     const uint64_t res_cap = (static_cast<uint64_t>(ef) + 1) & ~1ull;
-    // bitmap mode: the popped-key list moves to per-CTA global scratch when it would cost residency (see the kernel)
-    const bool res_global = vis == kVisGlobalBitmap && ctas_for(smem_lists) < 32;
-    const uint64_t smem = vis == kVisSmemHash ? smem_hash : (res_global ? smem_lists - res_cap * 8 : smem_lists);
+    // global modes: the popped-key list moves to per-CTA global scratch when it would cost residency (see the kernel)
+    const bool res_global = vis != kVisSmemHash && ctas_for(smem_lists + merge_smem) < 32;
+    uint64_t smem = vis == kVisSmemHash ? smem_hash : (res_global ? smem_lists - res_cap * 8 : smem_lists);
+    smem = (smem + 15) & ~15ull;
+    p.merge_off = static_cast<uint32_t>(smem);
+    smem += merge_smem;
     if (smem > ix->smem_optin) {
         char buf[256];
         snprintf(buf, sizeof buf, "search needs %llu bytes of shared memory per query (ef=%u, m=%u); this device allows %zu. Lower ef.",
                  static_cast<unsigned long long>(smem), ef, g.m, ix->smem_optin);
         return fail(ZVDB_ERR_UNSUPPORTED, buf);
     }
-    p.slots = static_cast<uint32_t>(slots); p.hash_words = static_cast<uint32_t>(slots);
-    // L2 prefetch, automatic = the rows of a pop's later gather batches, in bitmap mode with rows of at most 1 KiB
+    p.slots = static_cast<uint32_t>(slots); p.hash_words = static_cast<uint32_t>(hash_words);
+    // L2 prefetch, automatic = the rows of a pop's later gather batches, in the global modes with rows of at most 1 KiB
     // (+2..4 % on a graph that reaches every row; wider rows are bandwidth bound); off in shared-hash mode (small
     // ef: the extra issue slots cost 1-2 %). Prefetching the evaluated neighbours' adjacency rows measured no gain
     // anywhere and stays a variant. A/B: profiles/r01_k1_prefetch_ab.jsonl.
-    p.prefetch = ix->prefetch_mode == 0 ? ((vis == kVisGlobalBitmap && cpl <= 2) ? 1u : 0u) : ix->prefetch_mode - 1u;
+    p.prefetch = ix->prefetch_mode == 0 ? ((vis != kVisSmemHash && cpl <= 2) ? 1u : 0u) : ix->prefetch_mode - 1u;
     p.cand_cap = static_cast<uint32_t>(cand_cap);
-    // One warp per query. When shared memory already caps residency at <= 16 warps per SM, use the
-    // variant that keeps twice as many row loads in flight per warp (more registers per thread).
-    bool wide = ctas_for(smem) <= 16;
-    if (ix->variant == 1) wide = false;
-    if (ix->variant == 2) wide = true;
+    // One warp per query; CTAs resident per SM: 32 (16 beyond 256 floats per row: registers), fewer if shared memory binds.
+    const uint64_t resident = std::min<uint64_t>(ctas_for(smem), cpl <= 2 ? 32 : 16) * ix->num_sms;
     unsigned grid = static_cast<unsigned>(nq);
-    if (vis == kVisGlobalBitmap) {
-        const uint64_t resident = std::min<uint64_t>(ctas_for(smem), wide ? 16 : 32) * ix->num_sms;
-        grid = static_cast<unsigned>(std::min<uint64_t>(nq, resident));          // persistent CTAs
-        // the bitmaps are per-CTA state shared by every launch on this handle: order launches from
+    if (vis != kVisSmemHash) {
+        grid = static_cast<unsigned>(std::min<uint64_t>(nq, resident));          // persistent CTAs, one visited table each
+        // the tables are per-CTA state shared by every launch on this handle: order launches from
         // different streams behind the previous user
         ZV_CUDA(cudaStreamWaitEvent(s, ix->bitmap_ev, 0));
-        const uint64_t bm_words = (g.n + 31) / 32;
-        const uint64_t need = grid * bm_words;
-        if (need > ix->bitmap_buf.cap) {
-            ZV_CUDA(ix->bitmap_buf.reserve(need));
-            ZV_CUDA(cudaMemsetAsync(ix->bitmap_buf.p, 0, ix->bitmap_buf.cap * sizeof(uint32_t), s));
+        if (vis == kVisGlobalBitmap) {
+            const uint64_t bm_words = (g.n + 31) / 32;
+            const uint64_t need = grid * bm_words;
+            if (need > ix->bitmap_buf.cap) {
+                ZV_CUDA(ix->bitmap_buf.reserve(need));
+                ZV_CUDA(cudaMemsetAsync(ix->bitmap_buf.p, 0, ix->bitmap_buf.cap * sizeof(uint32_t), s));
+            }
+            const uint64_t log_cap = (bound + 3) & ~3ull;                          // 16-byte aligned logs (read back as uint4)
+            ZV_CUDA(ix->vlog_buf.reserve(grid * log_cap));
+            p.gbitmap = ix->bitmap_buf.p; p.glog = ix->vlog_buf.p;
+            p.bm_words = static_cast<uint32_t>(bm_words); p.log_cap = static_cast<uint32_t>(log_cap);
+        } else {
+            // every slot reads kInvalidId between queries: the kernel leaves the tables it used wiped, whatever their
+            // pitch was, so only fresh memory is initialised here
+            const uint64_t need = grid * hash_words;
+            if (need > ix->gtable_buf.cap) {
+                ZV_CUDA(ix->gtable_buf.reserve(need));
+                ZV_CUDA(cudaMemsetAsync(ix->gtable_buf.p, 0xFF, ix->gtable_buf.cap * sizeof(uint32_t), s));
+            }
+            p.gtable = ix->gtable_buf.p;
         }
-        const uint64_t log_cap = (bound + 3) & ~3ull;                          // 16-byte aligned logs (read back as uint4)
-        ZV_CUDA(ix->vlog_buf.reserve(grid * log_cap));
         if (res_global) {
             ZV_CUDA(ix->res_buf.reserve(grid * res_cap));
             p.gres = ix->res_buf.p; p.res_cap = static_cast<uint32_t>(res_cap);
         }
-        p.gbitmap = ix->bitmap_buf.p; p.glog = ix->vlog_buf.p;
-        p.bm_words = static_cast<uint32_t>(bm_words); p.log_cap = static_cast<uint32_t>(log_cap);
+    }
+    if (fx) {
+        for (uint32_t i = 0; i < fx->world; ++i) p.peer_qflags[i] = fx->peer_qflags[i];
+        p.qflags = fx->qflags; p.gather = fx->gather; p.block_bytes = fx->block_bytes;
+        p.m_ids = fx->m_ids; p.m_dist = fx->m_dist; p.m_counts = fx->m_counts;
+        p.ex_world = fx->world; p.ex_rank = fx->rank; p.ex_epoch = fx->epoch;
+        if (vis == kVisSmemHash) {                        // CTA b searches query b and merges query b - lag, one wave behind
+            p.merge_lag = static_cast<uint32_t>(std::min<uint64_t>(resident, nq));
+            grid = static_cast<unsigned>(nq + p.merge_lag);
+        }
     }
     cudaError_t e;
     if (p.seeds) {                                        // K2 first: one warp per query, 4 per CTA
-        // the seeds are per-handle scratch like the bitmaps: order launches from different streams
-        if (vis != kVisGlobalBitmap) ZV_CUDA(cudaStreamWaitEvent(s, ix->bitmap_ev, 0));
+        // the seeds are per-handle scratch like the tables: order launches from different streams
+        if (vis == kVisSmemHash) ZV_CUDA(cudaStreamWaitEvent(s, ix->bitmap_ev, 0));
         e = launch_descend(g.metric, cpl, p, static_cast<unsigned>((nq + 3) / 4), s);
         ix->launches++;
         ZV_CUDA(e);
     }
-    if (vis == kVisSmemHash) e = wide ? launch_search_wv<true, kVisSmemHash>(g.metric, cpl, p, grid, smem, s)
-                                      : launch_search_wv<false, kVisSmemHash>(g.metric, cpl, p, grid, smem, s);
-    else e = wide ? launch_search_wv<true, kVisGlobalBitmap>(g.metric, cpl, p, grid, smem, s)
-                  : launch_search_wv<false, kVisGlobalBitmap>(g.metric, cpl, p, grid, smem, s);
+    if (vis == kVisSmemHash) e = launch_search_vis<kVisSmemHash>(g.metric, cpl, p, grid, smem, s);
+    else if (vis == kVisGlobalBitmap) e = launch_search_vis<kVisGlobalBitmap>(g.metric, cpl, p, grid, smem, s);
+    else e = launch_search_vis<kVisGlobalHash>(g.metric, cpl, p, grid, smem, s);
     ix->launches++;
     ZV_CUDA(e);
-    if (vis == kVisGlobalBitmap || p.seeds) ZV_CUDA(cudaEventRecord(ix->bitmap_ev, s));
+    if (vis != kVisSmemHash || p.seeds) ZV_CUDA(cudaEventRecord(ix->bitmap_ev, s));
     return ZVDB_OK;
 }
 
 // ---- K5: shard merge ------------------------------------------------------------------------
-
-struct MergeLess {
-    const uint64_t *gid;   // shared-memory copy of the candidates' global ids
-    __device__ __forceinline__ bool operator()(uint64_t x, uint64_t y) const {
-        const uint32_t dx = static_cast<uint32_t>(x >> 32), dy = static_cast<uint32_t>(y >> 32);
-        if (dx != dy) return dx < dy;
-        const uint32_t ix_ = static_cast<uint32_t>(x), iy = static_cast<uint32_t>(y);
-        if (ix_ == kInvalidId || iy == kInvalidId) return ix_ != kInvalidId && iy == kInvalidId;
-        return gid[ix_] < gid[iy];
-    }
-};
 
 // One CTA per query: gather the G shard lists into shared memory, bitonic-sort them by
 // (distance, global id), write the first k. The G lists are addressed as base + g * stride (bytes),
@@ -803,7 +833,7 @@ void zvdb_destroy(zvdb_index *ix) {
     cudaFree(ix->d_arena); cudaFree(ix->d_adj);
     if (ix->h_stage) cudaFreeHost(ix->h_stage);
     ix->q_buf.free_(); ix->dist_buf.free_(); ix->ids_buf.free_(); ix->cnt_buf.free_();
-    ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_(); ix->res_buf.free_();
+    ix->pops_buf.free_(); ix->evals_buf.free_(); ix->scat_rows.free_(); ix->scat_ids.free_(); ix->bitmap_buf.free_(); ix->vlog_buf.free_(); ix->res_buf.free_(); ix->gtable_buf.free_();
     ix->d_level.free_(); ix->d_upper_base.free_(); ix->d_upper_adj.free_(); ix->seeds_buf.free_();
     ix->bf_xhi.free_(); ix->bf_xlo.free_(); ix->bf_xnorm.free_(); ix->bf_qhi.free_(); ix->bf_qlo.free_(); ix->bf_part.free_(); ix->bf_glists.free_(); ix->bf_segs.free_(); ix->bf_seg_off.free_();
     delete ix;
@@ -1353,10 +1383,11 @@ int zvdb_sync_device(zvdb_index *ix) {
 int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
     const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u, bfm = (variant >> 4) & 3u;
-    if (width > 2 || vis > 2 || bfm > 2 || variant > 4095 || ((variant >> 8) & 7u) > 4)
-        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = 0 auto/1 narrow/2 wide, bits 2-3 = 0 auto/1 shared hash/2 global bitmap, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-10 = L2 prefetch 0 auto/1 off/2 rows/3 adjacency/4 both, bit 11 = stage page-locked host buffers through device copies");
-    ix->prefetch_mode = (variant >> 8) & 7u; ix->stage_host_buffers = (variant >> 11) & 1u;
-    ix->variant = width; ix->visited_mode = vis; ix->bf_mode = bfm; ix->bf_filter = (variant >> 6) & 1u; ix->bf_epilogue = (variant >> 7) & 1u;
+    if (width > 2 || bfm > 2 || variant > 8191 || ((variant >> 8) & 7u) > 4)
+        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = accepted and ignored (round 1's load-width variants are gone: never faster in any automatically chosen mode), bits 2-3 = visited set 0 auto/1 shared-memory hash/2 global bitmap/3 global hash, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-10 = L2 prefetch 0 auto/1 off/2 rows/3 adjacency/4 both, bit 11 = stage page-locked host buffers through device copies, bit 12 = sharded step as three launches (search, flag, merge) instead of the fused one");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->prefetch_mode = (variant >> 8) & 7u; ix->stage_host_buffers = (variant >> 11) & 1u; ix->legacy_exchange = (variant >> 12) & 1u;
+    ix->visited_mode = vis; ix->bf_mode = bfm; ix->bf_filter = (variant >> 6) & 1u; ix->bf_epilogue = (variant >> 7) & 1u;
     return ZVDB_OK;
 }
 
@@ -1624,6 +1655,8 @@ struct zvdb_exchange {
     uint64_t flags_off = 0;
     uint8_t *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t **d_peer_flags = nullptr;   // device array of world pointers
+    uint64_t qflags_off = 0;         // per-query flag rows [nq_max][8] u32 (fused step): slot r of row q = last epoch rank r published for q
+    uint64_t nq_max = 0;
     uint32_t epoch = 0;
     bool opened = false;
 };
@@ -1639,7 +1672,9 @@ int zvdb_exchange_create(zvdb_exchange **out, int device, uint32_t world, uint32
     ex->device = device; ex->world = world; ex->rank = rank;
     ex->cap_bytes = zvdb_shard_block_bytes(nq_max, k_max) * world;
     ex->flags_off = 2 * ex->cap_bytes;
-    const size_t total = ex->flags_off + static_cast<size_t>(world) * kFlagPitch * sizeof(uint32_t);
+    ex->qflags_off = ex->flags_off + static_cast<size_t>(8) * kFlagPitch * sizeof(uint32_t);
+    ex->nq_max = nq_max;
+    const size_t total = ex->qflags_off + static_cast<size_t>(nq_max) * 8 * sizeof(uint32_t);
     cudaError_t e = cudaMalloc(&ex->local, total);
     if (e == cudaSuccess) e = cudaMemset(ex->local, 0, total);
     if (e == cudaSuccess) e = cudaMalloc(&ex->d_peer_flags, 8 * sizeof(uint32_t *));
@@ -1706,13 +1741,27 @@ int zvdb_search_batch_exchange(zvdb_index *ix, zvdb_exchange *ex, const float *d
     const uint64_t half = (epoch & 1) * ex->cap_bytes;           // double buffered: a peer may already be one call ahead
     uint8_t *blocks[8];
     for (uint32_t g = 0; g < ex->world; ++g) blocks[g] = ex->peer[g] + half + block * ex->rank;
-    if (ix->g.n == 0 || !ix->g.has_entry) {
+    const bool empty = ix->g.n == 0 || !ix->g.has_entry;
+    if (!empty) {
+        int rc = sync_device_locked(ix);
+        if (rc) return rc;
+    }
+    if (!ix->legacy_exchange && nq <= ex->nq_max) {
+        // ONE launch: search, peer stores, per-query flags, and -- one wave behind -- the merge of every query whose
+        // flag row is complete (an empty shard runs the same kernel and publishes zero results per query)
+        FusedExchange fx{};
+        for (uint32_t g = 0; g < ex->world; ++g) fx.peer_qflags[g] = reinterpret_cast<uint32_t *>(ex->peer[g] + ex->qflags_off);
+        fx.qflags = reinterpret_cast<const uint32_t *>(ex->local + ex->qflags_off);
+        fx.gather = ex->local + half; fx.block_bytes = block;
+        fx.m_ids = out_ids; fx.m_dist = out_dist; fx.m_counts = out_counts;
+        fx.world = ex->world; fx.rank = ex->rank; fx.epoch = epoch;
+        return launch_search(ix, d_queries, nq, k, ef, nullptr, nullptr, nullptr, nullptr, nullptr, ex->world, ex->rank, s, blocks, ex->world, &fx);
+    }
+    if (empty) {
         // an empty shard still publishes count 0 for every query (memset through the peer mappings)
         for (uint32_t g = 0; g < ex->world; ++g) ZV_CUDA(cudaMemsetAsync(blocks[g] + nq * k * 12, 0, nq * sizeof(uint32_t), s));
     } else {
-        int rc = sync_device_locked(ix);
-        if (rc) return rc;
-        rc = launch_search(ix, d_queries, nq, k, ef, nullptr, nullptr, nullptr, nullptr, nullptr, ex->world, ex->rank, s, blocks, ex->world);
+        int rc = launch_search(ix, d_queries, nq, k, ef, nullptr, nullptr, nullptr, nullptr, nullptr, ex->world, ex->rank, s, blocks, ex->world);
         if (rc) return rc;
     }
     exchange_signal_kernel<<<1, 32, 0, s>>>(ex->d_peer_flags, ex->world, ex->rank, kFlagPitch, epoch);

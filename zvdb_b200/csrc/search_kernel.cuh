@@ -70,6 +70,24 @@ struct SearchParams {
     // later gather batch (bitmap mode), bit 1 = the adjacency rows of the neighbours a pop evaluates -- one of
     // them is the next pop whenever the prediction from the window head fails.
     uint32_t prefetch;
+    // VIS_GLOBAL_HASH: [gridDim.x][hash_words] open-addressing tables in global memory (sized by ef*m, not by n: they
+    // stay L2-resident), every slot kInvalidId between queries
+    uint32_t *gtable;
+    // Fused exchange + merge, on when ex_world > 0: after a query's top-k went into block `ex_rank` of every
+    // peer's gather buffer (peer_blocks above), lane g publishes ex_epoch in slot ex_rank of peer g's per-query flag row
+    // (st.release.sys over NVLink); one wave later the same CTA slot merges an earlier query: it waits until the flag
+    // row of that query shows ex_epoch from every rank (ld.acquire.sys), then sorts the ex_world * k candidates of the
+    // LOCAL gather buffer by (distance, global id) and writes the first k to m_ids / m_dist / m_counts. One launch per
+    // sharded step; no signal kernel, no merge kernel, no collective.
+    uint32_t *peer_qflags[8];    // peer g's flag array [nq_max][8], mapped
+    const uint32_t *qflags;      // this rank's own flag array
+    const uint8_t *gather;       // this rank's gather buffer (the parity half of this epoch): ex_world blocks
+    uint64_t block_bytes;        // bytes between two ranks' blocks
+    uint64_t *m_ids; float *m_dist; uint32_t *m_counts;   // merged results [nq][k] / [nq]
+    uint32_t ex_world, ex_rank, ex_epoch;
+    uint32_t merge_p2;           // next_pow2(ex_world * k)
+    uint32_t merge_lag;          // one-CTA-per-query grids: CTA b merges query b - merge_lag (grid = nq + merge_lag)
+    uint32_t merge_off;          // byte offset of the merge scratch in dynamic shared memory
 };
 
 enum : int { kMetricL2 = 0, kMetricCos = 1, kMetricDot = 2 };
@@ -382,26 +400,89 @@ __global__ void __launch_bounds__(128) descend_kernel(const SearchParams p) {
     if (lane == 0) p.seeds[q] = make_uint4(entry, __float_as_uint(d0), ndesc, 0u);
 }
 
-enum : int { kVisSmemHash = 0, kVisGlobalBitmap = 1 };
+enum : int { kVisSmemHash = 0, kVisGlobalBitmap = 1, kVisGlobalHash = 2 };
+
+// Order of the shard merge (K5): by distance, then by GLOBAL id (gid[] is the shared-memory copy of the candidates'
+// ids, the key's low word its index); unused slots (low word kInvalidId) sort last.
+struct MergeLess {
+    const uint64_t *gid;
+    __device__ __forceinline__ bool operator()(uint64_t x, uint64_t y) const {
+        const uint32_t dx = static_cast<uint32_t>(x >> 32), dy = static_cast<uint32_t>(y >> 32);
+        if (dx != dy) return dx < dy;
+        const uint32_t ix_ = static_cast<uint32_t>(x), iy = static_cast<uint32_t>(y);
+        if (ix_ == kInvalidId || iy == kInvalidId) return ix_ != kInvalidId && iy == kInvalidId;
+        return gid[ix_] < gid[iy];
+    }
+};
+
+// Fused exchange, receiving side: one warp merges query q of this step from the LOCAL gather buffer (filled by every
+// rank's search epilogue through its peer mapping) once all ex_world ranks have published ex_epoch for q.
+__device__ __forceinline__ void merge_one_query(const SearchParams &p, uint32_t q, uint64_t *keys, uint32_t lane) {
+    if (lane < p.ex_world) {
+        const uint32_t *f = p.qflags + static_cast<size_t>(q) * 8 + lane;
+        uint32_t v, spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (static_cast<int32_t>(v - p.ex_epoch) >= 0) break;
+            if (++spins > 8) __nanosleep(spins > 64 ? 1000 : 100);
+        }
+    }
+    __syncwarp();
+    const uint32_t k = p.k, total = p.ex_world * k, p2 = p.merge_p2;
+    uint64_t *gid = keys + p2;
+    const size_t nk = static_cast<size_t>(p.nq) * k;
+    uint32_t valid = 0;
+    for (uint32_t i = lane; i < p2; i += 32) {
+        uint64_t key = ~0ull;
+        if (i < total) {
+            const uint32_t gsh = i / k, j = i - gsh * k;
+            const uint8_t *blk = p.gather + gsh * p.block_bytes;
+            const size_t src = static_cast<size_t>(q) * k + j;
+            gid[i] = __ldcg(reinterpret_cast<const uint64_t *>(blk) + src);          // L2: the bytes came in over NVLink
+            const uint32_t cnt = __ldcg(reinterpret_cast<const uint32_t *>(blk + nk * 12) + q);
+            if (j < cnt) {
+                key = (static_cast<uint64_t>(float_to_ordered(__ldcg(reinterpret_cast<const float *>(blk + nk * 8) + src))) << 32) | i;
+                ++valid;
+            }
+        }
+        keys[i] = key;
+    }
+    bitonic_sort_u64(keys, p2, MergeLess{gid});
+    valid = __reduce_add_sync(kFullMask, valid);
+    const uint32_t nres = min(valid, k);
+    for (uint32_t r = lane; r < k; r += 32) {
+        const size_t o = static_cast<size_t>(q) * k + r;
+        uint64_t oid = ~0ull; float od = 0.0f;
+        if (r < nres) { const uint64_t key = keys[r]; oid = gid[static_cast<uint32_t>(key)]; od = ordered_to_float(static_cast<uint32_t>(key >> 32)); }
+        p.m_ids[o] = oid; p.m_dist[o] = od;
+    }
+    if (lane == 0) p.m_counts[q] = nres;
+    __syncwarp();
+}
 
 // VIS selects the exact visited set:
 //   kVisSmemHash     open-addressing table in shared memory (small ef*m: everything on chip);
-//   kVisGlobalBitmap one bit per node in global memory, one atomicOr per neighbour (a single round
-//                    trip, no probing). Shared memory then holds only the candidate lists, so
-//                    residency stays high at large ef. The CTA is persistent, owns one bitmap and
-//                    wipes it after each query from its log of set ids.
-template <int CPL, int METRIC, bool WIDE, int VIS>
-__global__ void __launch_bounds__(32, (WIDE ? (CPL <= 2 ? 16 : 8) : (CPL <= 2 ? 32 : 16)))
+//   kVisGlobalHash   the same table in global memory, sized by ef*m and therefore L2-resident whatever n is: one
+//                    atomicCAS per neighbour, issued together with the row gathers, further probes only on a
+//                    collision; wiped with coalesced 16-byte stores when the query ends (no log). Shared memory holds
+//                    only the candidate lists, so residency stays at 32 queries per SM at any ef;
+//   kVisGlobalBitmap one bit per node in global memory, one atomicOr per neighbour (a single round trip, never a
+//                    probe), n/8 bytes per resident CTA, wiped from a log of the set ids (round 1's large-ef path,
+//                    kept as an A/B variant).
+// In the global modes the CTA is persistent and owns one table.
+template <int CPL, int METRIC, int VIS>
+__global__ void __launch_bounds__(32, (CPL <= 2 ? 32 : 16))
 search_layer0_kernel(const SearchParams p) {
-    constexpr int U = Unroll<CPL, WIDE>::value;
+    constexpr int U = Unroll<CPL, false>::value;
     constexpr uint32_t LPR = 32 / U;                            // lanes holding the same row after the reduce
+    constexpr bool GLOBAL_VIS = VIS != kVisSmemHash;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // Two layouts of the same arrays (same total). Bitmap mode: the fixed-size scratch first, at compile-time offsets
+    // Two layouts of the same arrays (same total). Global modes: the fixed-size scratch first, at compile-time offsets
     // (no address arithmetic on the hot path; measured +7..16 % at ef >= 128). Shared-hash mode keeps the lists first:
     // there the other order pushes the 64-register variants into spills (measured -12..19 %).
     uint64_t *res, *cand, *pool;
     uint32_t *todo, *rank_ex, *table;
-    if constexpr (VIS == kVisGlobalBitmap) {
+    if constexpr (GLOBAL_VIS) {
         pool = reinterpret_cast<uint64_t *>(smem_raw);              // [kPoolCap] pending pushes, unsorted
         todo = reinterpret_cast<uint32_t *>(pool + kPoolCap);       // [32] unvisited neighbour ids of the current pass (16-byte aligned)
         rank_ex = todo + 32;                                        // [kPoolCap] merge scratch
@@ -409,9 +490,9 @@ search_layer0_kernel(const SearchParams p) {
         // below 32 queries per SM (ef > 256) they go to per-CTA global scratch (L2) instead of shared memory:
         // ef=512: 9.1 -> 5.0 KB per query, 22 -> 32 resident queries per SM, +20..27 % QPS.
         uint64_t *lists = reinterpret_cast<uint64_t *>(rank_ex + kPoolCap);
-        if (p.gres) { res = p.gres + static_cast<size_t>(blockIdx.x) * p.res_cap; cand = lists; }
-        else { res = lists; cand = lists + ((p.ef + 1u) & ~1u); }   // [cand_cap] sorted window lives in [h, h+ns); final-sort scratch
-        table = nullptr;
+        res = lists;                                                // (global modes address the popped keys through res_at())
+        cand = p.gres ? lists : lists + ((p.ef + 1u) & ~1u);        // [cand_cap] sorted window lives in [h, h+ns); final-sort scratch
+        table = VIS == kVisGlobalHash ? p.gtable + static_cast<size_t>(blockIdx.x) * p.hash_words : nullptr;
     } else {
         res = reinterpret_cast<uint64_t *>(smem_raw);
         cand = res + ((p.ef + 1u) & ~1u);                           // (keeps todo 16-byte aligned)
@@ -423,11 +504,21 @@ search_layer0_kernel(const SearchParams p) {
     uint32_t *bitmap = VIS == kVisGlobalBitmap ? p.gbitmap + static_cast<size_t>(blockIdx.x) * p.bm_words : nullptr;
     uint32_t *vlog = VIS == kVisGlobalBitmap ? p.glog + static_cast<size_t>(blockIdx.x) * p.log_cap : nullptr;
 
+    // Where popped key i lives. In the global modes the address is rebuilt from kernel parameters at each use (one
+    // uniform multiply-add) instead of holding a generic 64-bit pointer live across the pop loop (it spilled).
+    auto res_at = [&](uint32_t i) -> uint64_t * {
+        if constexpr (GLOBAL_VIS) {
+            if (p.gres) return p.gres + static_cast<size_t>(blockIdx.x) * p.res_cap + i;
+        }
+        return res + i;
+    };
+
     const uint32_t lane = threadIdx.x;
     const float4 *__restrict__ arena = p.arena;
     const uint32_t pass_w = min(p.m, 32u);
 
-    for (uint32_t q = blockIdx.x; q < p.nq; q += gridDim.x) {   // persistent when gridDim.x < nq
+    for (uint32_t q = blockIdx.x;; q += gridDim.x) {            // persistent when gridDim.x < nq
+    if (q < p.nq) {
     // Query -> registers, chunked like an arena row, packed in pairs for the f32x2 pipe.
     Chunk2 qv[CPL];
     load_query<CPL>(qv, p.queries + static_cast<size_t>(q) * p.dim, p.dim, lane);
@@ -438,7 +529,8 @@ search_layer0_kernel(const SearchParams p) {
 
     // hnsw.zig:208-209: push the entry point, mark it visited
     uint32_t np = 0, h = 0, ns = 0, npool = 1, nev = 1;   // pops, window start, window length, pool fill, evaluations
-    {
+    if (p.n == 0) { npool = 0; nev = 0; }                 // an empty shard (sharded step): nothing to pop, zero results
+    else {
         uint32_t entry = p.entry;
         float d0;
         if (p.seeds == nullptr) {
@@ -449,8 +541,8 @@ search_layer0_kernel(const SearchParams p) {
         }
         if (lane == 0) {
             pool[0] = pack_key(d0, entry);
-            if (VIS == kVisSmemHash) visited_insert(table, p.slots, entry);
-            else { atomicOr(bitmap + (entry >> 5), 1u << (entry & 31)); vlog[0] = entry; }
+            if (VIS == kVisGlobalBitmap) { atomicOr(bitmap + (entry >> 5), 1u << (entry & 31)); vlog[0] = entry; }
+            else visited_insert(table, p.slots, entry);
         }
     }
     uint64_t worst = ~0ull;            // largest key of a FULL window: worse pushes can never be popped
@@ -482,7 +574,7 @@ search_layer0_kernel(const SearchParams p) {
             if (lane == 0) pool[slot] = pool[npool - 1];
             --npool;
         }
-        if (lane == 0) res[np] = cur_key;                        // :214
+        if (lane == 0) *res_at(np) = cur_key;                    // :214
         ++np;
         const uint32_t cur = key_id(cur_key);
         const uint32_t cap = p.ef - np;                          // only this many more pops can ever happen
@@ -504,15 +596,21 @@ search_layer0_kernel(const SearchParams p) {
                 pref_id = ns > 0 ? key_id(cand[h]) : kInvalidId;
                 pref_nb = (pref_id != kInvalidId && lane < p.m) ? __ldg(p.adj + static_cast<size_t>(pref_id) * p.m + lane) : kInvalidId;
             }
-            if constexpr (VIS == kVisGlobalBitmap) {
-                // Large-ef path: the visited test is an L2/HBM round trip (one atomicOr per neighbour), so the
+            if constexpr (GLOBAL_VIS) {
+                // Large-ef path: the visited test is an L2/HBM round trip (one atomic per neighbour), so the
                 // rows of the first U neighbours are requested TOGETHER with it instead of after it: one
                 // dependent memory trip per pop less. Rows of already-visited neighbours are fetched in vain
                 // (a few per cent on a well-connected graph); later chunks are fetched only if they hold a
                 // fresh neighbour. Results and counters are those of the compact-then-gather path.
                 const bool valid = nb != kInvalidId;
                 uint32_t old = 0;
-                if (valid) old = atomicOr(bitmap + (nb >> 5), 1u << (nb & 31));
+                if constexpr (VIS == kVisGlobalBitmap) {
+                    if (valid) old = atomicOr(bitmap + (nb >> 5), 1u << (nb & 31));
+                } else {
+                    // first probe at the home slot: kInvalidId back = it was free and now holds nb (fresh), nb back =
+                    // seen before, anything else = a collision, settled by further probes in resolve()
+                    if (valid) old = atomicCAS(table + __umulhi(nb * 0x9E3779B1u, p.slots), kInvalidId, nb);
+                }
                 const unsigned vmask = __ballot_sync(kFullMask, valid);
                 if (vmask == 0) continue;
                 const uint32_t nvalid = 32u - __clz(vmask);              // padding sits at the tail of the row
@@ -522,9 +620,25 @@ search_layer0_kernel(const SearchParams p) {
                 unsigned fmask = 0;
                 bool resolved = false;
                 auto resolve = [&]() {                                    // first use of the atomics' result
-                    const bool fresh = valid && ((old >> (nb & 31)) & 1u) == 0;         // :217, :221
+                    bool fresh;
+                    if constexpr (VIS == kVisGlobalBitmap) {
+                        fresh = valid && ((old >> (nb & 31)) & 1u) == 0;                // :217, :221
+                    } else {
+                        bool pending = valid && old != kInvalidId && old != nb;
+                        uint32_t hslot = __umulhi(nb * 0x9E3779B1u, p.slots);           // (recomputed: not kept live across the gather)
+                        while (__any_sync(kFullMask, pending)) {                        // linear probing, rare past the first slot
+                            if (pending) {
+                                hslot = (hslot + 1 == p.slots) ? 0 : hslot + 1;
+                                old = atomicCAS(table + hslot, kInvalidId, nb);
+                                pending = old != kInvalidId && old != nb;
+                            }
+                        }
+                        fresh = valid && old == kInvalidId;
+                    }
                     fmask = __ballot_sync(kFullMask, fresh);
-                    if (fresh) vlog[nev + __popc(fmask & ((1u << lane) - 1u))] = nb;
+                    if constexpr (VIS == kVisGlobalBitmap) {
+                        if (fresh) vlog[nev + __popc(fmask & ((1u << lane) - 1u))] = nb;
+                    }
                     nev += __popc(fmask);
                     resolved = true;
                 };
@@ -596,14 +710,14 @@ search_layer0_kernel(const SearchParams p) {
     uint64_t *sorted = cand;                                     // the window is dead now
     const uint32_t p2 = next_pow2(np);
     for (uint32_t i = lane; i < p2; i += 32)
-        sorted[i] = i < np ? ((res[i] & 0xFFFFFFFF00000000ull) | i) : ~0ull;
+        sorted[i] = i < np ? ((*res_at(i) & 0xFFFFFFFF00000000ull) | i) : ~0ull;
     bitonic_sort_u64(sorted, p2);
     const uint32_t nres = min(np, p.k);
     for (uint32_t r = lane; r < p.k; r += 32) {
         const size_t o = static_cast<size_t>(q) * p.k + r;
         uint64_t oid = ~0ull; float od = 0.0f;
         if (r < nres) {
-            const uint64_t key = res[static_cast<uint32_t>(sorted[r])];
+            const uint64_t key = *res_at(static_cast<uint32_t>(sorted[r]));
             oid = static_cast<uint64_t>(key_id(key)) * p.id_stride + p.id_base;
             od = key_dist(key);
         }
@@ -625,6 +739,12 @@ search_layer0_kernel(const SearchParams p) {
         if (p.pops) p.pops[q] = np;
         if (p.evals) p.evals[q] = nev + (p.seeds ? __ldg(p.seeds + q).z : 0u);
     }
+    if (p.ex_world) {
+        // publish: every lane's peer stores above are ordered before the flag by the warp barrier + the release store
+        __syncwarp();
+        if (lane < p.ex_world)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_qflags[lane] + static_cast<size_t>(q) * 8 + p.ex_rank), "r"(p.ex_epoch) : "memory");
+    }
     if (VIS == kVisGlobalBitmap) {       // wipe exactly the words this query set
         __syncwarp();
         const uint32_t nev4 = nev & ~3u;                 // the log is 16-byte aligned: four ids per load
@@ -643,7 +763,21 @@ search_layer0_kernel(const SearchParams p) {
         if (lane < nev - nev4) bitmap[vlog[nev4 + lane] >> 5] = 0u;
         // the __syncwarp below orders these stores before the next query's atomics on the same words (same warp)
     }
+    if (VIS == kVisGlobalHash) {         // wipe the whole table: coalesced 16-byte stores, hash_words is a multiple of 4
+        __syncwarp();
+        uint4 *t4 = reinterpret_cast<uint4 *>(table);
+        for (uint32_t i = lane; i < p.hash_words / 4; i += 32) t4[i] = make_uint4(kInvalidId, kInvalidId, kInvalidId, kInvalidId);
+    }
     __syncwarp();
+    }   // q < nq
+
+    if (p.ex_world) {
+        // fused merge, one wave behind the search: persistent grids merge the query this CTA searched one iteration
+        // ago (q - gridDim.x), one-CTA-per-query grids the query merge_lag CTAs back (grid = nq + merge_lag)
+        const uint32_t lag = GLOBAL_VIS ? gridDim.x : p.merge_lag;
+        if (q >= lag && q - lag < p.nq) merge_one_query(p, q - lag, reinterpret_cast<uint64_t *>(smem_raw + p.merge_off), lane);
+    }
+    if (q >= p.nq) break;
     }   // persistent query loop
 }
 

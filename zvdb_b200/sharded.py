@@ -6,10 +6,13 @@ under streaming insert). Every rank holds an independent per-shard index -- buil
 own insert on that shard's rows in global-id order -- and searches the FULL query batch on it; the
 per-shard top-k are then exchanged once and merged by (distance, global id):
 
-  * ``exchange="p2p"``  (default on CUDA): the search kernel's epilogue stores each shard's top-k
-    straight into every peer's gather buffer over NVLink (CUDA IPC mappings), a flag kernel publishes
-    completion, and the merge kernel waits on the flags -- no collective call at all
+  * ``exchange="p2p"``  (default on CUDA): ONE kernel launch per step. The search kernel's epilogue
+    stores each shard's top-k straight into every peer's gather buffer over NVLink (CUDA IPC
+    mappings) and publishes a per-query flag in every peer; one wave later the same kernel merges
+    each query whose flags are complete -- no collective call, no second launch
     (zvdb_search_batch_exchange);
+  * ``exchange="p2p3"``: round 1's form of the same exchange as three launches (search with peer
+    stores, a flag kernel, a merge kernel that waits on the flags), kept for A/B;
   * ``exchange="nccl"``: search into a packed block, ONE ``all_gather_into_tensor`` of the blocks,
     then the merge kernel (the formulation north_star states; also the baseline the fused path is
     measured against).
@@ -145,13 +148,15 @@ class ShardedHNSW:
         self.group = group
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
-        if exchange not in ("p2p", "nccl"):
-            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if exchange not in ("p2p", "p2p3", "nccl"):
+            raise ValueError("exchange must be 'p2p', 'p2p3' or 'nccl'")
         self.exchange = exchange
         self.m = m
         self.n_total = 0
         if backend is None:
             self.index = HNSW(m, ef_construction, metric=metric, device=self.rank if device is None else device)
+            if exchange == "p2p3":
+                self.index.set_kernel_variant(0x1000)          # bit 12: the sharded step as three launches
             self.backend = CudaBackend(self.index, self.rank, self.world)
         else:
             self.index = None
@@ -189,7 +194,7 @@ class ShardedHNSW:
         import torch.distributed as dist
         ef = ef or k
         e = ef_per_shard if ef_per_shard is not None else per_shard_ef(ef, k, self.world)
-        if self.exchange == "p2p" and hasattr(self.backend, "search_exchange"):
+        if self.exchange in ("p2p", "p2p3") and hasattr(self.backend, "search_exchange"):
             if not self._exchange_open or self.backend._cap[0] < nq or self.backend._cap[1] < k:
                 self.backend.close()
                 self.backend.open_exchange(max(nq, 1), k, self.group)

@@ -205,3 +205,53 @@ def test_gpu_descent_large_batch_and_bitmap_mode(zv, oracle):
     _check(zv, O, h, X, Q, 10, 32, up)
     _check(zv, O, h, X, Q[:600], 10, 300, up)
     h.deinit()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric_name", ["l2", "cos"])
+def test_gpu_descent_on_a_quality_graph_with_a_built_hierarchy(zv, oracle, metric_name):
+    """Round 2: builder graphs get upper layers too -- levels drawn like randomLevel
+    (hnsw.zig:172-180), layer l = the same builder on the rows of level >= l (zvdb_b200/builder.py build_hierarchy) --
+    so K2 has something worth walking. Descent + layer-0 search through the C ABI == orc_descend + orc_search on the
+    exported hierarchy, bit for bit; and at a small pop budget the descent finds more true neighbours than node 0 does."""
+    from zvdb_b200 import builder
+    zm, om = {"l2": (zv.METRIC_L2, oracle.METRIC_L2), "cos": (zv.METRIC_COSINE, oracle.METRIC_COS)}[metric_name]
+    n, dim, m = 20000, 32, 8
+    X = np.random.default_rng(71).standard_normal((n, dim), dtype=np.float32)
+    Q = np.random.default_rng(72).standard_normal((300, dim), dtype=np.float32)
+    h = zv.HNSW(m, 200, metric=zm)
+    builder.build_quality_graph(h, X, m, K=32)
+    levels, upper, start = builder.build_hierarchy(h, X, m, seed=3, K=32)
+    assert h.max_level == int(levels.max()) >= 8 and h.descent_start == start and h.entry_point == 0
+    lv, ub, ua = h.export_upper_layers()
+    assert np.array_equal(lv, levels) and np.array_equal(ua, upper)
+    # every list of layer l holds only nodes that have layer l, and never the node itself
+    for layer in (1, 2, 5):
+        S = np.nonzero(levels >= layer)[0]
+        lists = ua[ub[S].astype(np.int64) + (layer - 1)]
+        valid = lists != INV
+        assert np.all(levels[lists[valid]] >= layer)
+        assert not np.any(lists == S[:, None].astype(np.uint32))
+    Xs = np.stack([h.point(i) for i in range(n)]).astype(np.float32)
+    adj, _ = h.export_layer(0)
+    up = (lv, ub, ua, h.max_level, h.descent_start)
+    gt, _ = oracle.bruteforce(Xs, Q, 10, metric=zm)
+
+    def recall(ids):
+        return float(np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(Q))]))
+
+    plain = h.search_batch(Q, 10, 16, counters=True)
+    h.set_descent(True)
+    for k, ef in ((10, 16), (10, 64), (5, 300)):
+        ids, dist, counts, pops, evals = h.search_batch(Q, k, ef, counters=True)
+        ref = oracle.search_graph(Xs, adj, Q, ef, k, dist_mode=oracle.DIST_TREE | om, heap_mode=oracle.HEAP_DET, upper=up)
+        assert np.array_equal(counts, ref["counts"]) and np.array_equal(pops, ref["pops"]) and np.array_equal(evals, ref["evals"])
+        assert np.array_equal(ids, ref["ids"].astype(np.uint64))
+        assert np.array_equal(dist.view(np.uint32), ref["dist"].view(np.uint32))
+        seq = oracle.search_graph(Xs, adj, Q, ef, k, dist_mode=oracle.DIST_SEQ | om, heap_mode=oracle.HEAP_ZIG, upper=up)
+        np.testing.assert_allclose(dist, seq["dist"], rtol=RTOL, atol=1e-30)
+    with_descent = h.search_batch(Q, 10, 16)
+    r0, r1 = recall(plain[0]), recall(with_descent[0])
+    print(f"recall@10 at 16 pops ({metric_name}): from node 0 {r0:.3f}, after the descent {r1:.3f}")
+    assert r1 > r0
+    h.deinit()

@@ -53,16 +53,21 @@ def test_single_rank_sharded_equals_plain_search(zv, oracle, exchange):
 
 
 @pytest.mark.parametrize("k,ef", [(10, 16), (10, 300), (100, 100)])
-def test_fused_step_with_more_queries_than_resident_ctas(zv, k, ef):
+def test_fused_step_with_more_queries_than_resident_ctas(zv, oracle, k, ef):
     """The one-launch sharded step merges one wave behind the search: with 12 000 queries every kind of CTA occurs --
     search-only (first wave), search + merge, merge-only (the trailing wave of one-CTA-per-query grids) and, at
-    ef = 300, persistent CTAs that merge what they searched one iteration ago. Result = the plain search, bit for bit,
-    call after call (the gather buffer alternates its two halves, flags carry the epoch)."""
+    ef = 300, persistent CTAs that merge what they searched one iteration ago. Result = the plain search put through
+    the oracle's merge (one shard: the same entries, exact distance ties ordered by id instead of by pop order -- among
+    12 000 x 100 results a few such ties exist), bit for bit, call after call (the gather buffer alternates its two
+    halves, flags carry the epoch)."""
     from zvdb_b200.sharded import ShardedHNSW
     X, Q = _gauss(5000, 32, 111), _gauss(12000, 32, 112)
     sh = ShardedHNSW(16, 200, rank=0, world=1, device=0, exchange="p2p")
     sh.insert_batch(X)
-    want = sh.index.search_batch(Q, k, ef)
+    plain = sh.index.search_batch(Q, k, ef)
+    d, i, c = oracle.merge_topk(plain[1][None], plain[0][None], plain[2][None])
+    want = (i, d, c)
+    assert np.array_equal(np.sort(plain[0], axis=1), np.sort(i, axis=1))
     for rep in range(3):
         got = sh.search_batch(Q, k, ef)
         for a, b in zip(want, got):

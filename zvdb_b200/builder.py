@@ -2,8 +2,9 @@
 
 Candidate generation (approximate k-NN ids) feeds zvdb_build_from_candidates, whose CUDA kernels
 (csrc/builder.cuh) re-rank every candidate with exact distances and choose the <= m neighbours.
-Candidates may therefore come from a cheap, inexact source: here a chunked torch GEMM + top-k on
-the GPU (library plumbing, outside every timed region). No reference counterpart: the reference's
+Candidates may therefore come from any source: since round 2 the repo's own exact k-NN kernel
+(`knn_candidates_k4`; round 1's chunked torch bf16 GEMM + top-k is kept as `knn_candidates_torch` for A/B), outside
+every timed region. No reference counterpart: the reference's
 producer is HNSW.insert.
 
 The GEMM source is O(n^2): fine at 1M rows (18 s), out of reach for the 12.5M-row shards of C4.
@@ -32,16 +33,87 @@ def knn_candidates_torch(X: np.ndarray, K: int, device, chunk: int = 8192, dtype
     return out
 
 
-def build_quality_graph(h, X: np.ndarray, m: int, K: int = 64, device=None, chunk: int = 8192):
-    """Fill index `h` with a graph built on the GPU from K candidates per node."""
+def knn_candidates_k4(X: np.ndarray, K: int, device, metric: int = 0, chunk: int = 32768):
+    """ids[n, K] (int32, on `device`) of the EXACT K nearest rows of every row under `metric` (self included, at rank 0
+    unless it ties), from the repo's own exact k-NN kernel (K4: tcgen05 3xTF32 GEMM + fused top-k + exact re-rank)
+    instead of a library GEMM + top-k. The rows go into a scratch handle (no graph) that is dropped afterwards."""
+    import torch
+    from .hnsw import HNSW
+    n = len(X)
+    K = min(K, n)
+    tmp = HNSW(1, 0, metric=metric, device=device.index or 0)
+    try:
+        tmp.load_graph(X, np.zeros(n + 1, np.uint64), np.zeros(0, np.uint32), 0)      # rows only
+        tmp.sync_device()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        out = torch.empty((n, K), dtype=torch.int32, device=device)
+        ids = torch.empty((min(chunk, n), K), dtype=torch.int64, device=device)
+        dist = torch.empty((min(chunk, n), K), dtype=torch.float32, device=device)
+        cnt = torch.empty(min(chunk, n), dtype=torch.int32, device=device)
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            q = torch.from_numpy(np.ascontiguousarray(X[s:e], np.float32)).to(device)
+            tmp.bruteforce_knn_device(q.data_ptr(), e - s, K, ids.data_ptr(), dist.data_ptr(), cnt.data_ptr(), stream=stream)
+            out[s:e] = ids[:e - s].to(torch.int32)
+            torch.cuda.synchronize(device)
+            del q
+    finally:
+        tmp.deinit()
+    return out
+
+
+def build_quality_graph(h, X: np.ndarray, m: int, K: int = 64, device=None, chunk: int = 8192, source: str = "k4"):
+    """Fill index `h` with a graph built on the GPU from K candidates per node. source = "k4": exact candidates from the
+    repo's own brute-force kernel; "torch": round 1's bf16 library GEMM + top-k (kept for A/B)."""
     import torch
     device = device or torch.device("cuda", h.device)
     K = min(K, 128, max(1, len(X)))
-    cand = knn_candidates_torch(X, K, device, chunk)
+    if source == "k4":
+        cand = knn_candidates_k4(X, K, device, metric=h.metric)
+    else:
+        cand = knn_candidates_torch(X, K, device, chunk)
     torch.cuda.synchronize(device)
     h.build_from_candidates(X, K=K, cand_device_ptr=cand.data_ptr())
     del cand
     torch.cuda.empty_cache()
+
+
+def draw_levels(n: int, seed: int = 0, p: float = 0.5, cap: int = 31) -> np.ndarray:
+    """Node levels as the reference draws them (randomLevel, hnsw.zig:172-180): geometric with p = 1/2, capped at 31."""
+    lv = np.random.default_rng(seed).geometric(1.0 - p, n) - 1
+    return np.minimum(lv, cap).astype(np.uint8)
+
+
+def build_hierarchy(h, X: np.ndarray, m: int, levels=None, seed: int = 0, K: int = 64, layer_builder=None, log=None):
+    """Give a builder graph the layers >= 1 that the reference's insert maintains (hnsw.zig:78, :88-108) and its search
+    never reads (:216), so that the descent (K2, zvdb_set_descent) has something worth walking: node levels drawn like
+    randomLevel, and layer l = the SAME builder run on the rows whose level is >= l (ids mapped back to the full index).
+    The descent starts at the first node of maximum level. Layer 0 and the entry point (node 0) are untouched.
+    Returns (levels u8[n], upper_adj u32[n_lists, m], start)."""
+    import torch
+    from .hnsw import HNSW
+    n = len(X)
+    levels = draw_levels(n, seed) if levels is None else np.ascontiguousarray(levels, np.uint8)
+    layer_builder = layer_builder or (lambda ht, rows: build_quality_graph(ht, rows, m, K=K))
+    base = np.cumsum(levels.astype(np.int64)) - levels
+    upper = np.full((int(levels.astype(np.int64).sum()), m), 0xFFFFFFFF, np.uint32)
+    mx = int(levels.max(initial=0))
+    for layer in range(1, mx + 1):
+        S = np.nonzero(levels >= layer)[0]
+        if len(S) < 2:
+            continue                                    # a lone node keeps an empty list
+        ht = HNSW(m, 0, metric=h.metric, device=h.device)
+        layer_builder(ht, np.ascontiguousarray(X[S]))
+        adj, _ = ht.export_layer(0)
+        ht.deinit()
+        glob = np.where(adj == 0xFFFFFFFF, np.uint32(0xFFFFFFFF), S.astype(np.uint32)[np.minimum(adj, len(S) - 1)])
+        upper[base[S] + (layer - 1)] = glob
+        if log:
+            log(f"[builder] layer {layer}: {len(S)} rows linked")
+    start = int(np.argmax(levels == mx))
+    h.load_upper_layers(levels, upper, start)
+    torch.cuda.empty_cache()
+    return levels, upper, start
 
 
 def build_quality_graph_incremental(h, X: np.ndarray, m: int, K: int = 64, seed_rows: int = 131072, ef: int = 0,
@@ -74,7 +146,7 @@ def build_quality_graph_incremental(h, X: np.ndarray, m: int, K: int = 64, seed_
     join = max(0, min(int(join), (128 - K - keep) // m)) if refine_rounds > 0 else 0
     KT = K + keep + join * m
     cand = torch.full((n, KT), -1, dtype=torch.int32, device=device)         # 0xFFFFFFFF = padding, tolerated by the builder
-    cand[:n_cur, :K] = knn_candidates_torch(X[:n_cur], K, device)
+    cand[:n_cur, :K] = knn_candidates_k4(X[:n_cur], K, device, metric=h.metric)      # exact, from the repo's own K4
     torch.cuda.synchronize(device)
     h.build_from_candidates(X[:n_cur], K=KT, cand_device_ptr=cand.data_ptr())
     phases, searched = 1, [0]

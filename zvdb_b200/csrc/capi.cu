@@ -276,9 +276,14 @@ static int plan_visited(const zvdb_index *ix, uint32_t ef) {
     const uint64_t smem_lists = (((static_cast<uint64_t>(ef) + 1) & ~1ull) + cand_cap) * 8 + kPoolCap * 8 + 32 * 4 + kPoolCap * 4 + 16;
     const uint64_t smem_hash = smem_lists + slots * 4;
     const uint64_t ctas = std::min<uint64_t>(32, (227ull * 1024) / (smem_hash + 1024));
-    // On chip while that still leaves >= 20 queries per SM; beyond that the same hash table per resident CTA in
-    // global memory (sized by ef * m, so it stays in L2 however many rows the index has).
-    int vis = (smem_hash <= ix->smem_optin && ctas >= 20) ? kVisSmemHash : kVisGlobalHash;
+    // On chip while that still leaves >= 20 queries per SM. Beyond that, in global memory, per resident CTA: the n-bit
+    // bitmap (one atomicOr per neighbour, never a second probe: the fastest form measured, profiles/r02_k1_visited_ab.jsonl)
+    // while the bitmaps of all resident CTAs fit a 1 GiB scratch budget (n <= 1.8 M rows at full residency); the hash
+    // table sized by ef * m (40 KB at ef = 512 whatever n is, 20-35 % slower: probes past the first slot are extra L2
+    // round trips on a pop's critical path) for larger shards, where n/8 bytes per CTA would cost gigabytes (1.5 MB per
+    // CTA, 7 GB per GPU on a 12.5 M-row C4 shard).
+    const uint64_t bitmap_bytes = (g.n + 31) / 32 * 4 * 32ull * static_cast<uint64_t>(ix->num_sms);
+    int vis = (smem_hash <= ix->smem_optin && ctas >= 20) ? kVisSmemHash : (bitmap_bytes <= (1ull << 30) ? kVisGlobalBitmap : kVisGlobalHash);
     if (ix->visited_mode == 1) vis = kVisSmemHash;
     if (ix->visited_mode == 2) vis = kVisGlobalBitmap;
     if (ix->visited_mode == 3) vis = kVisGlobalHash;
@@ -370,7 +375,11 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     const uint64_t resident = std::min<uint64_t>(ctas_for(smem), cpl <= 2 ? 32 : 16) * ix->num_sms;
     unsigned grid = static_cast<unsigned>(nq);
     if (vis != kVisSmemHash) {
-        grid = static_cast<unsigned>(std::min<uint64_t>(nq, resident));          // persistent CTAs, one visited table each
+        // persistent CTAs, one visited table each, with a static stride over the queries: size the grid so that every
+        // CTA gets the same number of queries (10 000 queries on 4 736 resident CTAs would leave 528 CTAs with three
+        // queries and the rest idle for a third of the launch; 3 334 CTAs with three each finish together)
+        const uint64_t rounds = (nq + resident - 1) / resident;
+        grid = static_cast<unsigned>(std::min<uint64_t>(resident, (nq + rounds - 1) / rounds));
         // the tables are per-CTA state shared by every launch on this handle: order launches from
         // different streams behind the previous user
         ZV_CUDA(cudaStreamWaitEvent(s, ix->bitmap_ev, 0));

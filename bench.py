@@ -88,11 +88,12 @@ def parse_args():
                                                             "implies --no-cpu")
     p.add_argument("--no-recall", action="store_true", help="skip the exact ground truth (K4 needs 2x the arena for its operand split: "
                                                             "a 100M-row index on one GPU has no room for it)")
-    p.add_argument("--e2e-input", default="replicated", choices=["sliced", "replicated"],
-                   help="N>1 e2e: each rank moves 1/N of the batch host->device and an all-gather over NVLink assembles it "
-                        "(every query crosses PCIe once), or every rank reads the whole batch over its own PCIe link "
-                        "(default; measured at N=2: 27.2 M QPS replicated vs 24.9 M sliced -- the zero-copy reads overlap the "
-                        "search, the sliced copy + all-gather run before it)")
+    p.add_argument("--e2e-input", default="owner", choices=["owner", "sliced", "replicated"],
+                   help="N>1 e2e: owner (default) = zvdb_search_batch_exchange_host: each rank copies in 1/N of the batch, the ONE fused "
+                        "kernel reads every query from its owner's HBM over NVLink, sends each shard's top-k only to the query's owner, and the "
+                        "owner writes its 1/N of the merged rows to the host (every query and every result row crosses PCIe once); "
+                        "sliced = round 1's 1/N copy + NCCL all-gather of the queries + all-gather step + 1/N copy out; "
+                        "replicated = every rank reads the whole batch and writes the whole result over its own PCIe link")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs under ncu)")
     p.add_argument("--no-track", action="store_true", help="N=1: skip the throughput track (second index from the incremental builder, "
                                                            "ef sweep) and the K4 timing that the default line carries")
@@ -447,7 +448,7 @@ def run_ours(args):
         if args.exchange in ("p2p", "p2p3"):
             if args.exchange == "p2p3":
                 h.set_kernel_variant(args.variant | 0x1000)
-            backend.open_exchange(nq, k, None)
+            backend.open_exchange(nq, k, None, dim_max=args.dim)
         else:
             blk = torch.empty(block_bytes(nq, k), dtype=torch.uint8, device=dev)
             gathered = torch.empty(world * block_bytes(nq, k), dtype=torch.uint8, device=dev)
@@ -599,7 +600,8 @@ def run_ours(args):
     h_dist = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     h_cnt = torch.empty(nq, dtype=torch.int32).pin_memory()
 
-    if world > 1 and args.e2e_input == "sliced":
+    e2e_mode = args.e2e_input if (world > 1 and args.exchange == "p2p") else ("replicated" if args.e2e_input == "owner" else args.e2e_input)
+    if world > 1 and e2e_mode == "sliced":
         per = -(-nq // world)                                  # rows of the batch that cross THIS rank's PCIe link
         lo, hi = min(nq, rank * per), min(nq, (rank + 1) * per)
         q_part = torch.zeros((per, args.dim), dtype=torch.float32, device=dev)
@@ -608,7 +610,11 @@ def run_ours(args):
     def e2e_step(b):
         if world == 1:      # the reference-facing call: zvdb_search_batch on HOST pointers
             h.search_batch_ptr(hq[b].data_ptr(), nq, args.dim, k, ef, h_ids.data_ptr(), h_dist.data_ptr(), h_cnt.data_ptr())
-        elif args.e2e_input == "sliced":
+        elif e2e_mode == "owner":
+            # gather to owner: this rank's PCIe link carries 1/N of the batch in and 1/N of the merged rows out; one launch
+            backend.search_exchange_host(hq[b].data_ptr(), nq, args.dim, k, ef_shard, h_ids.data_ptr(), h_dist.data_ptr(), h_cnt.data_ptr())
+            torch.cuda.current_stream().synchronize()
+        elif e2e_mode == "sliced":
             # every query crosses PCIe once: rank r copies rows [lo, hi) of the page-locked batch, one all-gather over
             # NVLink assembles the batch on every GPU, the sharded step runs on it, and rank r copies rows [lo, hi) of
             # the merged top-k (identical on all ranks) back to the page-locked result buffers
@@ -649,13 +655,20 @@ def run_ours(args):
         clocks["window"] = "warm-up + timed region + e2e loop (50 ms period)"
     if world > 1:
         dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
-    copies = 1 if (world == 1 or args.e2e_input == "sliced") else world      # how many times the batch / the result crosses PCIe
+    copies = 1 if (world == 1 or e2e_mode in ("sliced", "owner")) else world      # how many times the batch / the result crosses PCIe
+    step_name = "zvdb_search_batch_exchange" if args.exchange != "nccl" else "zvdb_search_batch_packed_device + all_gather + merge"
+    if world == 1:
+        api = "zvdb_search_batch (page-locked host pointers; the kernel reads the batch from and writes the results to host memory)"
+    elif e2e_mode == "owner":
+        api = (f"per rank: zvdb_search_batch_exchange_host on the page-locked batch: 1/{world} of the queries H2D, ONE fused kernel (queries read from "
+               f"their owners over NVLink, top-k sent to the owner only, owner merges), 1/{world} of the merged rows written to the host by the kernel")
+    elif e2e_mode == "sliced":
+        api = f"per rank: 1/{world} of the page-locked batch H2D + all-gather over NVLink + {step_name} + 1/{world} of the merged top-k D2H"
+    else:
+        api = f"per rank: {step_name} on page-locked host query/result buffers (read and written by the kernels over PCIe)"
     e2e = {"value": nq * args.steps / float(e_dt.item()), "unit": "queries/s", "h2d_bytes_per_step": nq * args.dim * 4 * copies,
-           "d2h_bytes_per_step": (nq * k * 12 + nq * 4) * copies,
-           "api": "zvdb_search_batch (page-locked host pointers; the kernel reads the batch from and writes the results to host memory)" if world == 1 else
-                  (f"per rank: 1/{world} of the page-locked batch H2D + all-gather over NVLink + zvdb_search_batch_{'exchange' if args.exchange != 'nccl' else 'packed_device + all_gather + merge'} + 1/{world} of the merged top-k D2H"
-                   if args.e2e_input == "sliced" else
-                   f"per rank: zvdb_search_batch_{'exchange' if args.exchange != 'nccl' else 'packed_device + all_gather + merge'} on page-locked host query/result buffers (read and written by the kernels over PCIe)")}
+           "d2h_bytes_per_step": (nq * k * 12 + nq * 4) * copies, "api": api}
+    e2e["mode"] = "single GPU" if world == 1 else e2e_mode
     if staged_qps is not None:
         e2e["staged_copies_qps"] = staged_qps
     if world > 1:
@@ -670,6 +683,16 @@ def run_ours(args):
     got_dist = (m_dist if world > 1 else d_dist).cpu().numpy().copy()
     got_cnt = (m_cnt if world > 1 else d_cnt).cpu().numpy().view(np.uint32).copy()
     got_evals = d_evals.cpu().numpy().view(np.uint32).copy() if world == 1 else None
+    if world > 1 and e2e_mode == "owner":      # the host step's rows (this rank's slice) against the device step's, same batch
+        e2e_step(0)
+        per_ = -(-nq // world)
+        lo_, hi_ = min(nq, rank * per_), min(nq, (rank + 1) * per_)
+        ok = bool(np.array_equal(h_ids[lo_:hi_].numpy().view(np.uint64), got_ids[lo_:hi_]) and
+                  np.array_equal(h_dist[lo_:hi_].numpy().view(np.uint32), got_dist[lo_:hi_].view(np.uint32)) and
+                  np.array_equal(h_cnt[lo_:hi_].numpy().view(np.uint32), got_cnt[lo_:hi_]))
+        okt = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        e2e["rows_equal_device_step_on_every_rank"] = bool(okt.item() == 1.0)
 
     if rank != 0:
         if world > 1:

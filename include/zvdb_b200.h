@@ -271,9 +271,11 @@ ZVDB_API int zvdb_merge_topk_packed_device(const void *d_blocks, uint32_t G, uin
  * its 64-byte CUDA IPC handle, and opens every peer's. zvdb_search_batch_exchange then runs the
  * shard-local search with an epilogue that stores the shard's top-k directly into block `rank` of
  * EVERY rank's gather buffer (peer-mapped st.global over NVLink/NVSwitch: the all-gather happens
- * inside the search kernel, no collective call), publishes a per-rank flag (release, system scope),
- * and launches the merge kernel, which waits on the G flags (acquire) before merging. All ranks
- * obtain the merged top-k. Ranks must call it the same number of times with the same nq and k. */
+ * inside the search kernel, no collective call) and publishes a per-query flag in every peer (release,
+ * system scope); one wave later the SAME kernel merges each query whose flag row is complete (acquire)
+ * by (distance, global id): one launch per step. (zvdb_set_kernel_variant bit 12 restores round 1's
+ * three launches: search, a per-rank flag kernel, a merge kernel that waits on the G flags.) All ranks
+ * obtain the merged top-k. Ranks must call it the same number of times with the same nq, k and variant. */
 typedef struct zvdb_exchange zvdb_exchange;
 ZVDB_API int zvdb_exchange_create(zvdb_exchange **out, int device, uint32_t world, uint32_t rank, uint64_t nq_max,
                                   uint32_t k_max);
@@ -283,6 +285,24 @@ ZVDB_API void zvdb_exchange_destroy(zvdb_exchange *ex);
 ZVDB_API int zvdb_search_batch_exchange(zvdb_index *ix, zvdb_exchange *ex, const float *d_queries, uint64_t nq,
                                         uint32_t k, uint32_t ef, uint64_t *out_ids, float *out_dist,
                                         uint32_t *out_counts, void *stream);
+
+/* The same sharded step from HOST buffers, every byte crossing PCIe once ("gather to owner"). The batch is cut into
+ * `world` slices of ceil(nq / world) queries; rank r
+ *   (1) copies slice r of h_queries to its own HBM (the only host-to-device bytes on its PCIe link),
+ *   (2) runs ONE kernel that reads every query from its owner's HBM over NVLink (after the owner's kernel has
+ *       announced its slice), searches the local shard, sends the shard's top-k for query q only to q's owner, and --
+ *       one wave behind -- merges the queries of slice r by (distance, global id),
+ *   (3) writes rows [r * per, (r + 1) * per) of h_ids / h_dist / h_counts (straight from the kernel when the buffers
+ *       are page-locked, zvdb_alloc_host; through a device staging copy otherwise). Rows of other slices are not
+ *       touched: across the `world` processes every result row is written exactly once.
+ * Asynchronous on `stream`; the exchange must come from zvdb_exchange_create_host (it holds the query slices).
+ * There is no reference counterpart (the reference has no sharding); results equal
+ * zvdb_search_batch_exchange's on the same batch. */
+ZVDB_API int zvdb_exchange_create_host(zvdb_exchange **out, int device, uint32_t world, uint32_t rank, uint64_t nq_max,
+                                       uint32_t k_max, uint32_t dim_max);
+ZVDB_API int zvdb_search_batch_exchange_host(zvdb_index *ix, zvdb_exchange *ex, const float *h_queries, uint64_t nq,
+                                             uint32_t dim, uint32_t k, uint32_t ef, uint64_t *h_ids, float *h_dist,
+                                             uint32_t *h_counts, void *stream);
 
 /* ---- misc ---------------------------------------------------------------------------------- */
 

@@ -78,6 +78,39 @@ def test_fused_step_with_more_queries_than_resident_ctas(zv, oracle, k, ef):
     sh.deinit()
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_step_single_rank(zv, oracle, pinned):
+    """zvdb_search_batch_exchange_host at world = 1: the rank owns the whole batch, copies it in, and the kernel (or the
+    staging copy, for pageable buffers) writes the merged rows to the host arrays. Equals the device-buffer step."""
+    from zvdb_b200.sharded import ShardedHNSW
+    X, Q = _gauss(6000, 64, 121), _gauss(1500, 64, 122)
+    sh = ShardedHNSW(16, 200, rank=0, world=1, device=0)
+    sh.insert_batch(X)
+    for k, ef in ((10, 24), (10, 200), (40, 40)):
+        want = sh.search_batch(Q, k, ef)
+        if pinned:
+            hq, hi_, hd, hc = (zv.PinnedArray(Q.shape, np.float32), zv.PinnedArray((len(Q), k), np.uint64),
+                               zv.PinnedArray((len(Q), k), np.float32), zv.PinnedArray(len(Q), np.uint32))
+            hq.array[:] = Q
+            sh.ensure_exchange(len(Q), k, 64)
+            import torch
+            for rep in range(2):
+                hi_.array[:] = 0
+                sh.backend.search_exchange_host(hq.array.ctypes.data, len(Q), 64, k, ef, hi_.array.ctypes.data, hd.array.ctypes.data, hc.array.ctypes.data)
+                torch.cuda.current_stream().synchronize()
+                got = (hi_.array.copy(), hd.array.copy(), hc.array.copy())
+                for a, b in zip(want, got):
+                    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+            for a in (hq, hi_, hd, hc):
+                a.free()
+        else:
+            lo, hi, ids, dist, counts = sh.search_batch_host_slice(Q, k, ef)
+            assert (lo, hi) == (0, len(Q))
+            for a, b in zip(want, (ids, dist, counts)):
+                assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    sh.deinit()
+
+
 def test_packed_merge_kernel_matches_oracle(zv, oracle):
     import torch
     from zvdb_b200.sharded import block_bytes, pack_block
@@ -118,9 +151,15 @@ def _worker(rank, world, port, outdir, n, dim, m, nq, k, ef):
         for rep in range(3):
             ids, d, c = sh.search_batch(Q, k, ef)
         out[exchange] = (ids, d, c)
+        if exchange == "p2p":                  # the host step (gather to owner): this rank's slice of the merged rows
+            for rep in range(2):
+                lo, hi, hids, hd, hc = sh.search_batch_host_slice(Q, k, ef)
+            out["host"] = (np.array([lo, hi]), hids, hd, hc)
         dist.barrier()
         sh.deinit()
-    np.savez(os.path.join(outdir, f"r{rank}.npz"), **{f"{e}_{nm}": a for e, t in out.items() for nm, a in zip(("ids", "dist", "counts"), t)})
+    host = out.pop("host")
+    np.savez(os.path.join(outdir, f"r{rank}.npz"), host_range=host[0], host_ids=host[1], host_dist=host[2], host_counts=host[3],
+             **{f"{e}_{nm}": a for e, t in out.items() for nm, a in zip(("ids", "dist", "counts"), t)})
     dist.barrier()
     dist.destroy_process_group()
 
@@ -144,3 +183,12 @@ def test_two_gpu_sharded_search_matches_the_sharded_oracle(zv, oracle):
             assert np.array_equal(got[r][f"{e}_counts"], c), (r, e)
             assert np.array_equal(got[r][f"{e}_ids"], i), (r, e)
             assert np.array_equal(got[r][f"{e}_dist"].view(np.uint32), d.view(np.uint32)), (r, e)
+    # host step: the two ranks' slices tile the batch and together are the oracle's merged result
+    covered = 0
+    for r in range(world):
+        lo, hi = (int(x) for x in got[r]["host_range"])
+        assert lo == covered
+        covered = hi
+        assert np.array_equal(got[r]["host_counts"], c[lo:hi]) and np.array_equal(got[r]["host_ids"], i[lo:hi])
+        assert np.array_equal(got[r]["host_dist"].view(np.uint32), d[lo:hi].view(np.uint32))
+    assert covered == nq

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libzvdb_b200.so")
+# ZVDB_B200_LIB points the binding at another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("ZVDB_B200_LIB") or os.path.join(_HERE, "lib", "libzvdb_b200.so")
 
 OK, ERR_OOM, ERR_NODE_NOT_FOUND, ERR_DIM_MISMATCH, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED = range(7)
 METRIC_L2, METRIC_COSINE, METRIC_DOT = 0, 1, 2
@@ -62,6 +63,8 @@ SIGNATURES = {
     "zvdb_search_batch_packed_device": (_i32, [_vp, _vp, _u64, _u32, _u32, _vp, _u64, _u64, _vp]),
     "zvdb_merge_topk_packed_device": (_i32, [_vp, _u32, _u64, _u32, _vp, _vp, _vp, _vp]),
     "zvdb_exchange_create": (_i32, [C.POINTER(_vp), _i32, _u32, _u32, _u64, _u32]),
+    "zvdb_exchange_create_host": (_i32, [C.POINTER(_vp), _i32, _u32, _u32, _u64, _u32, _u32]),
+    "zvdb_search_batch_exchange_host": (_i32, [_vp, _vp, _vp, _u64, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "zvdb_exchange_ipc_handle": (_i32, [_vp, _vp]),
     "zvdb_exchange_open_peers": (_i32, [_vp, _vp]),
     "zvdb_exchange_destroy": (None, [_vp]),

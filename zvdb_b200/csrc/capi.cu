@@ -298,6 +298,12 @@ struct FusedExchange {
     uint64_t block_bytes;
     uint64_t *m_ids; float *m_dist; uint32_t *m_counts;
     uint32_t world, rank, epoch;
+    // gather-to-owner (zvdb_search_batch_exchange_host): q_per > 0
+    uint32_t q_per = 0;
+    const float *peer_q[8] = {};
+    uint32_t *peer_sflags[8] = {};
+    const uint32_t *sflags = nullptr;
+    uint32_t sflag_pitch = 0;
 };
 
 // Device buffers in, device buffers out, no synchronisation. Caller holds the lock and has synced
@@ -320,6 +326,7 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     p.row_chunks = g.row_floats / 4;
     p.m = g.m; p.n = static_cast<uint32_t>(g.n); p.entry = static_cast<uint32_t>(g.entry); p.dim = g.dim;
     p.nq = static_cast<uint32_t>(nq); p.k = k; p.ef = ef;
+    if (g.n == 0) { p.ef = 0; p.row_chunks = 0; p.entry = 0; }   // an empty shard of a sharded step: no pop, no memory touched, zero results
     if (ix->descent && g.max_level > 0 && g.n > 0) {      // K2: start at the top node, walk down, then the beam
         int rcu = sync_upper_locked(ix);
         if (rcu) return rcu;
@@ -375,11 +382,11 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     const uint64_t resident = std::min<uint64_t>(ctas_for(smem), cpl <= 2 ? 32 : 16) * ix->num_sms;
     unsigned grid = static_cast<unsigned>(nq);
     if (vis != kVisSmemHash) {
-        // persistent CTAs, one visited table each, with a static stride over the queries: size the grid so that every
-        // CTA gets the same number of queries (10 000 queries on 4 736 resident CTAs would leave 528 CTAs with three
-        // queries and the rest idle for a third of the launch; 3 334 CTAs with three each finish together)
-        const uint64_t rounds = (nq + resident - 1) / resident;
-        grid = static_cast<unsigned>(std::min<uint64_t>(resident, (nq + rounds - 1) / rounds));
+        // persistent CTAs, one visited table each, static stride over the queries. (A grid balanced to equal rounds --
+        // 3 334 CTAs x 3 queries instead of 4 736 x 2.1 for a 10 000-query batch -- was measured in round 2: no change on a
+        // graph that reaches every row, 5-7 % slower on the L2-resident reference graph, which is bound by issue slots and
+        // wants every resident warp it can get.)
+        grid = static_cast<unsigned>(std::min<uint64_t>(nq, resident));
         // the tables are per-CTA state shared by every launch on this handle: order launches from
         // different streams behind the previous user
         ZV_CUDA(cudaStreamWaitEvent(s, ix->bitmap_ev, 0));
@@ -414,6 +421,8 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
         p.qflags = fx->qflags; p.gather = fx->gather; p.block_bytes = fx->block_bytes;
         p.m_ids = fx->m_ids; p.m_dist = fx->m_dist; p.m_counts = fx->m_counts;
         p.ex_world = fx->world; p.ex_rank = fx->rank; p.ex_epoch = fx->epoch;
+        p.q_per = fx->q_per; p.sflags = fx->sflags; p.sflag_pitch = fx->sflag_pitch;
+        for (uint32_t i = 0; i < fx->world; ++i) { p.peer_q[i] = fx->peer_q[i]; p.peer_sflags[i] = fx->peer_sflags[i]; }
         if (vis == kVisSmemHash) {                        // CTA b searches query b and merges query b - lag, one wave behind
             p.merge_lag = static_cast<uint32_t>(std::min<uint64_t>(resident, nq));
             grid = static_cast<unsigned>(nq + p.merge_lag);
@@ -1666,12 +1675,21 @@ struct zvdb_exchange {
     uint32_t **d_peer_flags = nullptr;   // device array of world pointers
     uint64_t qflags_off = 0;         // per-query flag rows [nq_max][8] u32 (fused step): slot r of row q = last epoch rank r published for q
     uint64_t nq_max = 0;
+    uint64_t qbuf_off = 0;           // host step: [2][nq_max][dim_max] f32, this rank's slice of the query batch (by epoch parity)
+    uint32_t dim_max = 0;
+    uint64_t *d_out_ids = nullptr; float *d_out_dist = nullptr; uint32_t *d_out_counts = nullptr;   // host step with pageable result buffers: staging
+    uint64_t out_cap = 0;
     uint32_t epoch = 0;
     bool opened = false;
 };
 static constexpr uint32_t kFlagPitch = 32;   // one flag per 128 bytes
 
 int zvdb_exchange_create(zvdb_exchange **out, int device, uint32_t world, uint32_t rank, uint64_t nq_max, uint32_t k_max) {
+    return zvdb_exchange_create_host(out, device, world, rank, nq_max, k_max, 0);
+}
+
+int zvdb_exchange_create_host(zvdb_exchange **out, int device, uint32_t world, uint32_t rank, uint64_t nq_max, uint32_t k_max,
+                              uint32_t dim_max) {
     if (!out) return fail(ZVDB_ERR_INVALID, "exchange: out is null");
     *out = nullptr;
     if (world == 0 || world > 8 || rank >= world) return fail(ZVDB_ERR_INVALID, "exchange: world must be 1..8 and rank < world");
@@ -1683,7 +1701,9 @@ int zvdb_exchange_create(zvdb_exchange **out, int device, uint32_t world, uint32
     ex->flags_off = 2 * ex->cap_bytes;
     ex->qflags_off = ex->flags_off + static_cast<size_t>(8) * kFlagPitch * sizeof(uint32_t);
     ex->nq_max = nq_max;
-    const size_t total = ex->qflags_off + static_cast<size_t>(nq_max) * 8 * sizeof(uint32_t);
+    ex->qbuf_off = (ex->qflags_off + static_cast<size_t>(nq_max) * 8 * sizeof(uint32_t) + 255) / 256 * 256;
+    ex->dim_max = dim_max;
+    const size_t total = ex->qbuf_off + 2 * static_cast<size_t>(nq_max) * dim_max * sizeof(float);
     cudaError_t e = cudaMalloc(&ex->local, total);
     if (e == cudaSuccess) e = cudaMemset(ex->local, 0, total);
     if (e == cudaSuccess) e = cudaMalloc(&ex->d_peer_flags, 8 * sizeof(uint32_t *));
@@ -1729,6 +1749,7 @@ void zvdb_exchange_destroy(zvdb_exchange *ex) {
         if (g != ex->rank && ex->peer[g]) cudaIpcCloseMemHandle(ex->peer[g]);
     cudaFree(ex->d_peer_flags);
     cudaFree(ex->local);
+    cudaFree(ex->d_out_ids); cudaFree(ex->d_out_dist); cudaFree(ex->d_out_counts);
     delete ex;
 }
 
@@ -1781,6 +1802,83 @@ int zvdb_search_batch_exchange(zvdb_index *ix, zvdb_exchange *ex, const float *d
                           reinterpret_cast<const uint32_t *>(ex->local + ex->flags_off), kFlagPitch, epoch);
     ix->launches++;
     return rc;
+}
+
+int zvdb_search_batch_exchange_host(zvdb_index *ix, zvdb_exchange *ex, const float *h_queries, uint64_t nq, uint32_t dim,
+                                    uint32_t k, uint32_t ef, uint64_t *h_ids, float *h_dist, uint32_t *h_counts, void *stream) {
+    if (!ix || !ex) return fail(ZVDB_ERR_INVALID, "null argument");
+    if (!ex->opened && ex->world > 1) return fail(ZVDB_ERR_INVALID, "exchange: peers not opened");
+    if (nq == 0) return ZVDB_OK;
+    if (!h_queries || !h_ids || !h_dist || !h_counts) return fail(ZVDB_ERR_INVALID, "search: null buffer");
+    if (k == 0) return fail(ZVDB_ERR_INVALID, "search: k must be >= 1");
+    if (ef == 0) ef = k;
+    if (ef < k) return fail(ZVDB_ERR_INVALID, "search: ef must be >= k");
+    if (dim == 0 || dim > ex->dim_max || nq > ex->nq_max)
+        return fail(ZVDB_ERR_INVALID, "exchange: created without a query buffer for this dim / batch size (zvdb_exchange_create_host)");
+    const uint64_t block = zvdb_shard_block_bytes(nq, k);
+    if (block * ex->world > ex->cap_bytes) return fail(ZVDB_ERR_INVALID, "exchange: nq * k exceeds the capacity the exchange was created with");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ZV_CUDA(cudaSetDevice(ix->device));
+    const bool empty = ix->g.n == 0 || !ix->g.has_entry;
+    if (!empty && dim != ix->g.dim) return fail(ZVDB_ERR_DIM_MISMATCH, "Mismatched dimensions in distance calculation");
+    if (!empty) {
+        int rc = sync_device_locked(ix);
+        if (rc) return rc;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t epoch = ++ex->epoch;
+    const uint64_t half = (epoch & 1) * ex->cap_bytes;
+    const uint64_t per = (nq + ex->world - 1) / ex->world;                       // queries per slice; rank r owns [r*per, (r+1)*per)
+    const uint64_t lo = std::min<uint64_t>(nq, per * ex->rank), hi = std::min<uint64_t>(nq, lo + per);
+    const uint64_t qhalf = ex->qbuf_off + (epoch & 1) * ex->nq_max * static_cast<uint64_t>(ex->dim_max) * sizeof(float);
+    // (1) this rank's slice of the batch: the only host-to-device bytes of the step on this PCIe link
+    if (hi > lo)
+        ZV_CUDA(cudaMemcpyAsync(ex->local + qhalf + lo * dim * sizeof(float), h_queries + lo * dim, (hi - lo) * dim * sizeof(float),
+                                cudaMemcpyHostToDevice, s));
+    // (2) results: straight into the caller's buffers when they are page-locked, else through device staging
+    auto mapped = [](const void *ptr, void **dptr) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+        *dptr = a.devicePointer;
+        return true;
+    };
+    void *di = nullptr, *dd = nullptr, *dc = nullptr;
+    const bool direct = mapped(h_ids, &di) && mapped(h_dist, &dd) && mapped(h_counts, &dc);
+    if (!direct) {
+        if (nq * k > ex->out_cap) {
+            ZV_CUDA(cudaStreamSynchronize(s));
+            cudaFree(ex->d_out_ids); cudaFree(ex->d_out_dist); cudaFree(ex->d_out_counts);
+            ex->d_out_ids = nullptr; ex->d_out_dist = nullptr; ex->d_out_counts = nullptr; ex->out_cap = 0;
+            ZV_CUDA(cudaMalloc(&ex->d_out_ids, nq * k * sizeof(uint64_t)));
+            ZV_CUDA(cudaMalloc(&ex->d_out_dist, nq * k * sizeof(float)));
+            ZV_CUDA(cudaMalloc(&ex->d_out_counts, nq * k * sizeof(uint32_t)));
+            ex->out_cap = nq * k;
+        }
+        di = ex->d_out_ids; dd = ex->d_out_dist; dc = ex->d_out_counts;
+    }
+    // (3) ONE launch: search on queries read from their owners, top-k to the owner only, the owner merges its slice
+    uint8_t *blocks[8];
+    for (uint32_t g = 0; g < ex->world; ++g) blocks[g] = ex->peer[g] + half + block * ex->rank;
+    FusedExchange fx{};
+    for (uint32_t g = 0; g < ex->world; ++g) {
+        fx.peer_qflags[g] = reinterpret_cast<uint32_t *>(ex->peer[g] + ex->qflags_off);
+        fx.peer_q[g] = reinterpret_cast<const float *>(ex->peer[g] + qhalf);
+        fx.peer_sflags[g] = reinterpret_cast<uint32_t *>(ex->peer[g] + ex->flags_off);
+    }
+    fx.qflags = reinterpret_cast<const uint32_t *>(ex->local + ex->qflags_off);
+    fx.sflags = reinterpret_cast<const uint32_t *>(ex->local + ex->flags_off); fx.sflag_pitch = kFlagPitch;
+    fx.gather = ex->local + half; fx.block_bytes = block;
+    fx.m_ids = static_cast<uint64_t *>(di); fx.m_dist = static_cast<float *>(dd); fx.m_counts = static_cast<uint32_t *>(dc);
+    fx.world = ex->world; fx.rank = ex->rank; fx.epoch = epoch; fx.q_per = static_cast<uint32_t>(per);
+    int rc = launch_search(ix, nullptr, nq, k, ef, nullptr, nullptr, nullptr, nullptr, nullptr, ex->world, ex->rank, s, blocks, ex->world, &fx);
+    if (rc) return rc;
+    if (!direct && hi > lo) {
+        ZV_CUDA(cudaMemcpyAsync(h_ids + lo * k, ex->d_out_ids + lo * k, (hi - lo) * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        ZV_CUDA(cudaMemcpyAsync(h_dist + lo * k, ex->d_out_dist + lo * k, (hi - lo) * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+        ZV_CUDA(cudaMemcpyAsync(h_counts + lo, ex->d_out_counts + lo, (hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    return ZVDB_OK;
 }
 
 }  // extern "C"

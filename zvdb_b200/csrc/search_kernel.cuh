@@ -88,6 +88,17 @@ struct SearchParams {
     uint32_t merge_p2;           // next_pow2(ex_world * k)
     uint32_t merge_lag;          // one-CTA-per-query grids: CTA b merges query b - merge_lag (grid = nq + merge_lag)
     uint32_t merge_off;          // byte offset of the merge scratch in dynamic shared memory
+    // Gather-to-owner form of the fused step (zvdb_search_batch_exchange_host), on when q_per > 0: the batch is cut
+    // into ex_world slices of q_per queries; rank o holds slice o of the QUERIES in its own HBM (it alone copied them
+    // from the host) and is the only rank that needs slice o of the RESULTS (it alone writes them to the host). So
+    // a warp reads its query from the owner's memory over NVLink (after the owner's kernel has announced that its
+    // slice landed: slice flag), sends its shard's top-k to the owner only, and only the owner merges the query.
+    // Every query and every result crosses PCIe once, and the exchange moves 1/ex_world of the all-gather's bytes.
+    uint32_t q_per;
+    const float *peer_q[8];      // rank o's query buffer [nq][dim] (rows of slice o valid), mapped
+    uint32_t *peer_sflags[8];    // peer g's slice flags [8] x pitch: slot r = last epoch whose slice r is in place
+    const uint32_t *sflags;      // this rank's slice flags
+    uint32_t sflag_pitch;
 };
 
 enum : int { kMetricL2 = 0, kMetricCos = 1, kMetricDot = 2 };
@@ -418,16 +429,19 @@ struct MergeLess {
 // Fused exchange, receiving side: one warp merges query q of this step from the LOCAL gather buffer (filled by every
 // rank's search epilogue through its peer mapping) once all ex_world ranks have published ex_epoch for q.
 __device__ __forceinline__ void merge_one_query(const SearchParams &p, uint32_t q, uint64_t *keys, uint32_t lane) {
-    if (lane < p.ex_world) {
-        const uint32_t *f = p.qflags + static_cast<size_t>(q) * 8 + lane;
-        uint32_t v, spins = 0;
-        for (;;) {
+    {
+        // Warp-uniform wait: every lane polls (lanes past ex_world re-read the last rank's flag) and the loop exits on a
+        // warp vote, so control flow never diverges. A divergent spin loop here made the compiler treat the whole
+        // persistent query loop as possibly diverged and wrap every shuffle / vote of the pop loop in WARPSYNC +
+        // collective bookkeeping: +12 % executed instructions, +10 % time on the L2-resident reference graph (round 2).
+        const uint32_t *f = p.qflags + static_cast<size_t>(q) * 8 + min(lane, p.ex_world - 1u);
+        for (uint32_t spins = 0;; ++spins) {
+            uint32_t v;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (static_cast<int32_t>(v - p.ex_epoch) >= 0) break;
-            if (++spins > 8) __nanosleep(spins > 64 ? 1000 : 100);
+            if (__all_sync(kFullMask, static_cast<int32_t>(v - p.ex_epoch) >= 0)) break;
+            if (spins > 8) __nanosleep(spins > 64 ? 1000 : 100);
         }
     }
-    __syncwarp();
     const uint32_t k = p.k, total = p.ex_world * k, p2 = p.merge_p2;
     uint64_t *gid = keys + p2;
     const size_t nk = static_cast<size_t>(p.nq) * k;
@@ -506,7 +520,13 @@ search_layer0_kernel(const SearchParams p) {
 
     // Where popped key i lives. In the global modes the address is rebuilt from kernel parameters at each use (one
     // uniform multiply-add) instead of holding a generic 64-bit pointer live across the pop loop (it spilled).
+    // Where popped key i lives. 128-float rows (every config but C3): one pointer held in registers. Wider rows: the
+    // address is rebuilt from kernel parameters at each use (one uniform multiply-add) -- there the generic 64-bit
+    // pointer, live across the pop loop, spilled; at 128 floats it does not and saves 2 %.
+    uint64_t *res_ptr = res;
+    if constexpr (GLOBAL_VIS) { if (p.gres) res_ptr = p.gres + static_cast<size_t>(blockIdx.x) * p.res_cap; }
     auto res_at = [&](uint32_t i) -> uint64_t * {
+        if constexpr (CPL == 1) return res_ptr + i;
         if constexpr (GLOBAL_VIS) {
             if (p.gres) return p.gres + static_cast<size_t>(blockIdx.x) * p.res_cap + i;
         }
@@ -516,12 +536,28 @@ search_layer0_kernel(const SearchParams p) {
     const uint32_t lane = threadIdx.x;
     const float4 *__restrict__ arena = p.arena;
     const uint32_t pass_w = min(p.m, 32u);
+    if (p.q_per && blockIdx.x == 0 && lane < p.ex_world && lane != p.ex_rank)   // our slice of the queries is in place (copied before this launch)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_sflags[lane] + static_cast<size_t>(p.ex_rank) * p.sflag_pitch), "r"(p.ex_epoch) : "memory");
 
     for (uint32_t q = blockIdx.x;; q += gridDim.x) {            // persistent when gridDim.x < nq
     if (q < p.nq) {
     // Query -> registers, chunked like an arena row, packed in pairs for the f32x2 pipe.
     Chunk2 qv[CPL];
-    load_query<CPL>(qv, p.queries + static_cast<size_t>(q) * p.dim, p.dim, lane);
+    const float *qsrc = p.queries;
+    if (p.q_per) {                                        // gather-to-owner: the query lives in its owner's HBM
+        const uint32_t owner = q / p.q_per;
+        qsrc = p.peer_q[owner];
+        if (owner != p.ex_rank) {                         // (our own slice was copied in before this kernel, stream order)
+            const uint32_t *f = p.sflags + static_cast<size_t>(owner) * p.sflag_pitch;
+            for (uint32_t spins = 0;; ++spins) {          // warp-uniform wait (all lanes poll the same word, exit on a vote)
+                uint32_t v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (__all_sync(kFullMask, static_cast<int32_t>(v - p.ex_epoch) >= 0)) break;
+                if (spins > 8) __nanosleep(spins > 64 ? 1000 : 100);
+            }
+        }
+    }
+    load_query<CPL>(qv, qsrc + static_cast<size_t>(q) * p.dim, p.dim, lane);
     if (VIS == kVisSmemHash) {
         for (uint32_t i = lane; i < p.slots; i += 32) table[i] = kInvalidId;
     }
@@ -529,8 +565,10 @@ search_layer0_kernel(const SearchParams p) {
 
     // hnsw.zig:208-209: push the entry point, mark it visited
     uint32_t np = 0, h = 0, ns = 0, npool = 1, nev = 1;   // pops, window start, window length, pool fill, evaluations
-    if (p.n == 0) { npool = 0; nev = 0; }                 // an empty shard (sharded step): nothing to pop, zero results
-    else {
+    // (An empty shard in a sharded step is launched with ef = 0 and row_chunks = 0: no pop, no row or adjacency access,
+    // zero results per query. A branch on p.n here cost 8 % in the global-visited modes: npool / nev no longer start
+    // as constants.)
+    {
         uint32_t entry = p.entry;
         float d0;
         if (p.seeds == nullptr) {
@@ -713,6 +751,8 @@ search_layer0_kernel(const SearchParams p) {
         sorted[i] = i < np ? ((*res_at(i) & 0xFFFFFFFF00000000ull) | i) : ~0ull;
     bitonic_sort_u64(sorted, p2);
     const uint32_t nres = min(np, p.k);
+    // receivers of this query's shard-local top-k: every rank (all-gather), or only the query's owner
+    const uint32_t g_lo = p.q_per ? q / p.q_per : 0u, g_hi = p.q_per ? g_lo + 1u : p.n_peers;
     for (uint32_t r = lane; r < p.k; r += 32) {
         const size_t o = static_cast<size_t>(q) * p.k + r;
         uint64_t oid = ~0ull; float od = 0.0f;
@@ -724,7 +764,7 @@ search_layer0_kernel(const SearchParams p) {
         if (p.n_peers == 0) { p.ids[o] = oid; p.dist[o] = od; }
         else {
             const size_t nk = static_cast<size_t>(p.nq) * p.k;
-            for (uint32_t g = 0; g < p.n_peers; ++g) {
+            for (uint32_t g = g_lo; g < g_hi; ++g) {
                 reinterpret_cast<uint64_t *>(p.peer_blocks[g])[o] = oid;
                 reinterpret_cast<float *>(p.peer_blocks[g] + nk * 8)[o] = od;
             }
@@ -734,7 +774,7 @@ search_layer0_kernel(const SearchParams p) {
         if (p.n_peers == 0) p.counts[q] = nres;
         else {
             const size_t nk = static_cast<size_t>(p.nq) * p.k;
-            for (uint32_t g = 0; g < p.n_peers; ++g) reinterpret_cast<uint32_t *>(p.peer_blocks[g] + nk * 12)[q] = nres;
+            for (uint32_t g = g_lo; g < g_hi; ++g) reinterpret_cast<uint32_t *>(p.peer_blocks[g] + nk * 12)[q] = nres;
         }
         if (p.pops) p.pops[q] = np;
         if (p.evals) p.evals[q] = nev + (p.seeds ? __ldg(p.seeds + q).z : 0u);
@@ -742,7 +782,7 @@ search_layer0_kernel(const SearchParams p) {
     if (p.ex_world) {
         // publish: every lane's peer stores above are ordered before the flag by the warp barrier + the release store
         __syncwarp();
-        if (lane < p.ex_world)
+        if (lane >= g_lo && lane < g_hi)
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_qflags[lane] + static_cast<size_t>(q) * 8 + p.ex_rank), "r"(p.ex_epoch) : "memory");
     }
     if (VIS == kVisGlobalBitmap) {       // wipe exactly the words this query set
@@ -775,7 +815,7 @@ search_layer0_kernel(const SearchParams p) {
         // fused merge, one wave behind the search: persistent grids merge the query this CTA searched one iteration
         // ago (q - gridDim.x), one-CTA-per-query grids the query merge_lag CTAs back (grid = nq + merge_lag)
         const uint32_t lag = GLOBAL_VIS ? gridDim.x : p.merge_lag;
-        if (q >= lag && q - lag < p.nq) merge_one_query(p, q - lag, reinterpret_cast<uint64_t *>(smem_raw + p.merge_off), lane);
+        if (q >= lag && q - lag < p.nq && (p.q_per == 0 || (q - lag) / p.q_per == p.ex_rank)) merge_one_query(p, q - lag, reinterpret_cast<uint64_t *>(smem_raw + p.merge_off), lane);
     }
     if (q >= p.nq) break;
     }   // persistent query loop

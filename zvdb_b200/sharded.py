@@ -103,10 +103,11 @@ class CudaBackend:
         return (ids.cpu().numpy().view(np.uint64), dist.cpu().numpy(), counts.cpu().numpy().view(np.uint32))
 
     # -- fused formulation ------------------------------------------------------------------------
-    def open_exchange(self, nq_max: int, k_max: int, group) -> None:
+    def open_exchange(self, nq_max: int, k_max: int, group, dim_max: int = 0) -> None:
+        """dim_max > 0 also reserves the query slices of the host step (search_exchange_host)."""
         import torch.distributed as dist
         torch = self.torch
-        L.check(L.lib().zvdb_exchange_create(C.byref(self.exchange), self.index.device, self.world, self.rank, nq_max, k_max))
+        L.check(L.lib().zvdb_exchange_create_host(C.byref(self.exchange), self.index.device, self.world, self.rank, nq_max, k_max, dim_max))
         mine = (C.c_uint8 * 64)()
         L.check(L.lib().zvdb_exchange_ipc_handle(self.exchange, mine))
         handles = [None] * self.world
@@ -116,7 +117,7 @@ class CudaBackend:
             handles[0] = bytes(mine)
         blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
         L.check(L.lib().zvdb_exchange_open_peers(self.exchange, blob))
-        self._cap = (nq_max, k_max)
+        self._cap = (nq_max, k_max, dim_max)
         if self.world > 1:
             dist.barrier(group=group)
 
@@ -131,6 +132,12 @@ class CudaBackend:
                                                    ids.data_ptr(), dist.data_ptr(), counts.data_ptr(),
                                                    torch.cuda.current_stream().cuda_stream))
         return ids, dist, counts
+
+    def search_exchange_host(self, q_ptr: int, nq: int, dim: int, k: int, ef: int, ids_ptr: int, dist_ptr: int, counts_ptr: int):
+        """zvdb_search_batch_exchange_host on raw HOST addresses: this rank copies in its slice of the batch and writes
+        its slice of the merged results (gather to owner); asynchronous on the current stream."""
+        L.check(L.lib().zvdb_search_batch_exchange_host(self.index._h, self.exchange, q_ptr, nq, dim, k, ef, ids_ptr, dist_ptr,
+                                                        counts_ptr, self.torch.cuda.current_stream().cuda_stream))
 
     def close(self) -> None:
         if self.exchange:
@@ -195,10 +202,7 @@ class ShardedHNSW:
         ef = ef or k
         e = ef_per_shard if ef_per_shard is not None else per_shard_ef(ef, k, self.world)
         if self.exchange in ("p2p", "p2p3") and hasattr(self.backend, "search_exchange"):
-            if not self._exchange_open or self.backend._cap[0] < nq or self.backend._cap[1] < k:
-                self.backend.close()
-                self.backend.open_exchange(max(nq, 1), k, self.group)
-                self._exchange_open = True
+            self.ensure_exchange(nq, k)
             return self.backend.search_exchange(d_queries, nq, k, e)
         block = self.backend.search_packed(d_queries, nq, k, e)
         if self.world == 1:
@@ -208,6 +212,16 @@ class ShardedHNSW:
             dist.all_gather_into_tensor(gathered, block, group=self.group)     # the ONE collective of the path
         return self.backend.merge_packed(gathered, nq, k)
 
+    def ensure_exchange(self, nq: int, k: int, dim: int = 0) -> None:
+        """(Re)open the peer-mapped exchange so that it holds nq x k results per rank and, for the host step, query slices
+        of `dim` floats. Collective: every rank must call it with the same arguments."""
+        cap = getattr(self.backend, "_cap", (0, 0, 0))
+        if not self._exchange_open or cap[0] < nq or cap[1] < k or cap[2] < dim:
+            self.backend.close()
+            self.backend.open_exchange(max(nq, cap[0] if self._exchange_open else 0, 1), max(k, cap[1] if self._exchange_open else 0), self.group,
+                                       dim_max=max(dim, cap[2] if self._exchange_open else 0))
+            self._exchange_open = True
+
     def search_batch(self, queries, k: int, ef: int = 0, ef_per_shard: Optional[int] = None):
         """Host arrays in, host arrays out: (ids u64 [nq,k] global, dist f32 [nq,k], counts u32 [nq])."""
         q = np.ascontiguousarray(queries, np.float32)
@@ -215,6 +229,27 @@ class ShardedHNSW:
             q = q.reshape(1, -1)
         out = self.search_batch_device(self.backend.to_device(q), q.shape[0], k, ef, ef_per_shard)
         return self.backend.to_host(*out)
+
+    def search_batch_host_slice(self, queries, k: int, ef: int = 0, ef_per_shard: Optional[int] = None):
+        """The host step (gather to owner): every rank passes the SAME host batch; rank r gets back
+        (lo, hi, ids[lo:hi], dist[lo:hi], counts[lo:hi]) -- its slice of the merged top-k of the whole index. Every query
+        and every result row crosses PCIe once over the whole job. CUDA backend only."""
+        import torch
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        nq, dim = q.shape
+        ef = ef or k
+        e = ef_per_shard if ef_per_shard is not None else per_shard_ef(ef, k, self.world)
+        self.ensure_exchange(nq, k, dim)
+        ids = np.full((nq, k), 0xFFFFFFFFFFFFFFFF, np.uint64)
+        dist = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        self.backend.search_exchange_host(q.ctypes.data, nq, dim, k, e, ids.ctypes.data, dist.ctypes.data, counts.ctypes.data)
+        torch.cuda.current_stream().synchronize()
+        per = -(-nq // self.world)
+        lo, hi = min(nq, per * self.rank), min(nq, per * (self.rank + 1))
+        return lo, hi, ids[lo:hi], dist[lo:hi], counts[lo:hi]
 
     def deinit(self) -> None:
         if hasattr(self.backend, "close"):

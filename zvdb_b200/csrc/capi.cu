@@ -278,12 +278,12 @@ static int plan_visited(const zvdb_index *ix, uint32_t ef) {
     const uint64_t ctas = std::min<uint64_t>(32, (227ull * 1024) / (smem_hash + 1024));
     // On chip while that still leaves >= 20 queries per SM. Beyond that, in global memory, per resident CTA: the n-bit
     // bitmap (one atomicOr per neighbour, never a second probe: the fastest form measured, profiles/r02_k1_visited_ab.jsonl)
-    // while the bitmaps of all resident CTAs fit a 1 GiB scratch budget (n <= 1.8 M rows at full residency); the hash
-    // table sized by ef * m (40 KB at ef = 512 whatever n is, 20-35 % slower: probes past the first slot are extra L2
-    // round trips on a pop's critical path) for larger shards, where n/8 bytes per CTA would cost gigabytes (1.5 MB per
-    // CTA, 7 GB per GPU on a 12.5 M-row C4 shard).
+    // while the bitmaps of all resident CTAs fit an 8 GiB scratch budget (n <= 14.5 M rows at full residency: a 12.5 M-row
+    // C4 shard still qualifies, 7.4 GB next to 6.4 GB of rows on a 180 GB part); the hash table sized by ef * m (40 KB per
+    // CTA at ef = 512 whatever n is, but 15-45 % slower: probes past the first slot are extra L2 round trips on a pop's
+    // critical path) for larger shards, where n/8 bytes per CTA would cost tens of gigabytes.
     const uint64_t bitmap_bytes = (g.n + 31) / 32 * 4 * 32ull * static_cast<uint64_t>(ix->num_sms);
-    int vis = (smem_hash <= ix->smem_optin && ctas >= 20) ? kVisSmemHash : (bitmap_bytes <= (1ull << 30) ? kVisGlobalBitmap : kVisGlobalHash);
+    int vis = (smem_hash <= ix->smem_optin && ctas >= 20) ? kVisSmemHash : (bitmap_bytes <= (8ull << 30) ? kVisGlobalBitmap : kVisGlobalHash);
     if (ix->visited_mode == 1) vis = kVisSmemHash;
     if (ix->visited_mode == 2) vis = kVisGlobalBitmap;
     if (ix->visited_mode == 3) vis = kVisGlobalHash;

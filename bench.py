@@ -537,8 +537,16 @@ def run_ours(args):
                 step(0, es)
             bb.record(); barrier()
             ms = a.elapsed_time(bb) / 3
-            sweep.append({"ef": e, "pops_per_shard": es, "qps": nq / (ms * 1e-3),
-                          "recall_at_10": None if gt is None else recall_at_k(m_ids.cpu().numpy().view(np.uint64), gt)})
+            got_m = m_ids.cpu().numpy().view(np.uint64)
+            d_m = m_dist.cpu().numpy()
+            sweep.append({"ef": e, "pops_per_shard": es, "ms_per_step": ms, "qps": nq / (ms * 1e-3),
+                          "recall_at_10": None if gt is None else recall_at_k(got_m, gt),
+                          # size-independent properties of the merged result (the oracle cannot follow to 100M rows): every list
+                          # full, sorted by distance, without duplicate ids; the checksum ties this run to the one-GPU run of the
+                          # same shards (scripts/c4_shards_one_gpu.py prints the same sum)
+                          "properties": {"counts_all_k": bool((m_cnt.cpu().numpy() == k).all()), "sorted": bool((np.diff(d_m, axis=1) >= 0).all()),
+                                         "ids_unique_per_query": bool(all(len(set(r.tolist())) == k for r in got_m[:2000]))},
+                          "merged_ids_checksum": int(m_ids.sum().item())})
     if args.sweep and rank == 0 and world == 1:
         sweep = []
         for e in (32, 64, 128, 256, 512):

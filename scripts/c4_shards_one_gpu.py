@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--build-threads", type=int, default=8)
+    ap.add_argument("--graph", default="reference", choices=["reference", "incremental"],
+                    help="per-shard graph: the reference's insert (host, shards in parallel) or the search-driven incremental builder (GPU, one shard after the other)")
     ap.add_argument("--min-free-gb", type=float, default=0.0, help="refuse to start with less free host memory than this")
     args = ap.parse_args()
 
@@ -73,9 +75,17 @@ def main():
             except Exception as e:   # noqa: BLE001
                 errs.append((s, repr(e)))
 
-    th = [threading.Thread(target=build_one, args=(s,)) for s in range(S)]
-    [t.start() for t in th]
-    [t.join() for t in th]
+    if args.graph == "incremental":
+        from zvdb_b200 import builder
+        for s in range(S):
+            Xs = bench.make_shard(args.rows, dim, s, S)
+            builder.build_quality_graph_incremental(hs[s], Xs, args.m)
+            del Xs
+            print(f"shard {s} built ({time.time() - t0:.0f}s)", file=sys.stderr, flush=True)
+    else:
+        th = [threading.Thread(target=build_one, args=(s,)) for s in range(S)]
+        [t.start() for t in th]
+        [t.join() for t in th]
     if errs:
         raise RuntimeError(f"shard build failed: {errs}")
     for h in hs:
@@ -128,7 +138,7 @@ def main():
         line = {"metric": "batched search QPS (id-sharded index held by one GPU)", "value": nq / (ms * 1e-3), "unit": "queries/s",
                 "n_gpus": 1, "shards": S, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "config": {"workload": f"{args.rows}x{dim} fp32 L2 synthetic Gaussian, M={args.m}, {nq}-query batch, k={k}, ef={ef} "
-                                       f"({e} pops/shard, {S} per-shard reference-insert indexes on one GPU, merge kernel, no exchange)",
+                                       f"({e} pops/shard, {S} per-shard {args.graph}-graph indexes on one GPU, merge kernel, no exchange)",
                            "evals_per_query_all_shards": evals, "build_seconds": build_s},
                 "roofline": {"bound": "hbm", "achieved": job_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": job_bytes / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,

@@ -34,6 +34,14 @@ extern fn zvdb_load(ix: *zvdb_index, path: [*:0]const u8) c_int;
 extern fn zvdb_alloc_host(bytes: usize) ?*anyopaque;
 extern fn zvdb_free_host(p: ?*anyopaque) void;
 extern fn zvdb_last_error() [*:0]const u8;
+// id-sharded deployment (one process per GPU): the fused one-launch step, device and host forms
+pub const zvdb_exchange = opaque {};
+pub extern fn zvdb_exchange_create_host(out: *?*zvdb_exchange, device: c_int, world: u32, rank: u32, nq_max: u64, k_max: u32, dim_max: u32) c_int;
+pub extern fn zvdb_exchange_ipc_handle(ex: *zvdb_exchange, handle64: *[64]u8) c_int;
+pub extern fn zvdb_exchange_open_peers(ex: *zvdb_exchange, handles: [*]const u8) c_int; // world x 64 bytes, rank order
+pub extern fn zvdb_exchange_destroy(ex: ?*zvdb_exchange) void;
+pub extern fn zvdb_search_batch_exchange(ix: *zvdb_index, ex: *zvdb_exchange, d_queries: [*]const f32, nq: u64, k: u32, ef: u32, out_ids: [*]u64, out_dist: [*]f32, out_counts: [*]u32, stream: ?*anyopaque) c_int;
+pub extern fn zvdb_search_batch_exchange_host(ix: *zvdb_index, ex: *zvdb_exchange, h_queries: [*]const f32, nq: u64, dim: u32, k: u32, ef: u32, h_ids: [*]u64, h_dist: [*]f32, h_counts: [*]u32, stream: ?*anyopaque) c_int;
 
 pub const Error = error{ OutOfMemory, NodeNotFound, DimMismatch, CudaError, Invalid, Unsupported };
 

@@ -79,8 +79,9 @@ def parse_args():
     p.add_argument("--variant", type=int, default=0, help="zvdb_set_kernel_variant bits (0 = automatic; e.g. 8 = global bitmap, 12 = global hash visited set)")
     p.add_argument("--cpu-sample", type=int, default=0, help="--impl reference: queries per step (0 = the whole batch, like a GPU step)")
     p.add_argument("--cpu-seconds", type=float, default=10.0, help="cpu_baseline leg: keep passing over the query batches for about this long")
-    p.add_argument("--exchange", default="p2p", choices=["p2p", "p2p3", "nccl"],
-                   help="N>1: p2p = ONE launch per step (search + peer stores + per-query flags + merge one wave behind), "
+    p.add_argument("--exchange", default="p2p", choices=["p2p", "p2pb", "p2p3", "nccl"],
+                   help="N>1: p2p = ONE launch per step (search + 128-byte self-validating records into the peers + merge one wave behind), "
+                        "p2pb = the same with result blocks + per-query release flags, "
                         "p2p3 = round 1's three launches (search with peer stores, flag kernel, merge kernel), nccl = search, one NCCL all-gather, merge kernel")
     p.add_argument("--descent", action="store_true", help="K2: walk the upper layers before the layer-0 search (extension; "
                                                           "needs upper layers: the reference graph has them)")
@@ -445,9 +446,11 @@ def run_ours(args):
         m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         m_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
         m_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
-        if args.exchange in ("p2p", "p2p3"):
+        if args.exchange in ("p2p", "p2pb", "p2p3"):
             if args.exchange == "p2p3":
                 h.set_kernel_variant(args.variant | 0x1000)
+            if args.exchange == "p2pb":
+                h.set_kernel_variant(args.variant | 0x2000)
             backend.open_exchange(nq, k, None, dim_max=args.dim)
         else:
             blk = torch.empty(block_bytes(nq, k), dtype=torch.uint8, device=dev)
@@ -470,9 +473,9 @@ def run_ours(args):
             h.search_batch_device(q.data_ptr(), nq, k, e, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(),
                                   d_pops.data_ptr(), d_evals.data_ptr(), stream=stream)
             launches[0] += 1
-        elif args.exchange in ("p2p", "p2p3"):
+        elif args.exchange in ("p2p", "p2pb", "p2p3"):
             backend.search_exchange(q, nq, k, e, out=(o_ids, o_dist, o_cnt))      # one fused launch (p2p3: search, signal, merge)
-            launches[0] += 1 if args.exchange == "p2p" else 3
+            launches[0] += 3 if args.exchange == "p2p3" else 1
         else:
             zvdb_b200._lib.check(zvdb_b200.lib().zvdb_search_batch_packed_device(h._h, q.data_ptr(), nq, k, e, blk.data_ptr(),
                                                                                  world, rank, stream))
@@ -608,7 +611,7 @@ def run_ours(args):
     h_dist = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     h_cnt = torch.empty(nq, dtype=torch.int32).pin_memory()
 
-    e2e_mode = args.e2e_input if (world > 1 and args.exchange == "p2p") else ("replicated" if args.e2e_input == "owner" else args.e2e_input)
+    e2e_mode = args.e2e_input if (world > 1 and args.exchange in ("p2p", "p2pb")) else ("replicated" if args.e2e_input == "owner" else args.e2e_input)
     if world > 1 and e2e_mode == "sliced":
         per = -(-nq // world)                                  # rows of the batch that cross THIS rank's PCIe link
         lo, hi = min(nq, rank * per), min(nq, (rank + 1) * per)

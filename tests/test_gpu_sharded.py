@@ -31,7 +31,7 @@ def _sharded_oracle(O, X, Q, world, m, k, e):
     return O.merge_topk(np.stack(D), np.stack(I), np.stack(Cn))
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "p2p3", "nccl"])
+@pytest.mark.parametrize("exchange", ["p2p", "p2pb", "p2p3", "nccl"])
 def test_single_rank_sharded_equals_plain_search(zv, oracle, exchange):
     from zvdb_b200.sharded import ShardedHNSW
     X, Q = _gauss(6000, 64, 101), _gauss(200, 64, 102)
@@ -52,8 +52,9 @@ def test_single_rank_sharded_equals_plain_search(zv, oracle, exchange):
     sh.deinit()
 
 
-@pytest.mark.parametrize("k,ef", [(10, 16), (10, 300), (100, 100)])
-def test_fused_step_with_more_queries_than_resident_ctas(zv, oracle, k, ef):
+@pytest.mark.parametrize("exchange", ["p2p", "p2pb"])
+@pytest.mark.parametrize("k,ef", [(10, 16), (10, 300), (100, 100), (14, 20), (15, 20)])      # 14 / 15 results: one / two record lines
+def test_fused_step_with_more_queries_than_resident_ctas(zv, oracle, k, ef, exchange):
     """The one-launch sharded step merges one wave behind the search: with 12 000 queries every kind of CTA occurs --
     search-only (first wave), search + merge, merge-only (the trailing wave of one-CTA-per-query grids) and, at
     ef = 300, persistent CTAs that merge what they searched one iteration ago. Result = the plain search put through
@@ -62,7 +63,7 @@ def test_fused_step_with_more_queries_than_resident_ctas(zv, oracle, k, ef):
     halves, flags carry the epoch)."""
     from zvdb_b200.sharded import ShardedHNSW
     X, Q = _gauss(5000, 32, 111), _gauss(12000, 32, 112)
-    sh = ShardedHNSW(16, 200, rank=0, world=1, device=0, exchange="p2p")
+    sh = ShardedHNSW(16, 200, rank=0, world=1, device=0, exchange=exchange)
     sh.insert_batch(X)
     plain = sh.index.search_batch(Q, k, ef)
     d, i, c = oracle.merge_topk(plain[1][None], plain[0][None], plain[2][None])
@@ -145,7 +146,7 @@ def _worker(rank, world, port, outdir, n, dim, m, nq, k, ef):
                             device_id=torch.device("cuda", rank))
     X, Q = _gauss(n, dim, 104), _gauss(nq, dim, 105)
     out = {}
-    for exchange in ("p2p", "p2p3", "nccl"):
+    for exchange in ("p2p", "p2pb", "p2p3", "nccl"):
         sh = ShardedHNSW(m, 200, device=rank, exchange=exchange)
         sh.insert_batch(X)
         for rep in range(3):
@@ -179,7 +180,7 @@ def test_two_gpu_sharded_search_matches_the_sharded_oracle(zv, oracle):
     X, Q = _gauss(n, dim, 104), _gauss(nq, dim, 105)
     d, i, c = _sharded_oracle(oracle, X, Q, world, m, k, per_shard_ef(ef, k, world))
     for r in range(world):
-        for e in ("p2p", "p2p3", "nccl"):
+        for e in ("p2p", "p2pb", "p2p3", "nccl"):
             assert np.array_equal(got[r][f"{e}_counts"], c), (r, e)
             assert np.array_equal(got[r][f"{e}_ids"], i), (r, e)
             assert np.array_equal(got[r][f"{e}_dist"].view(np.uint32), d.view(np.uint32)), (r, e)

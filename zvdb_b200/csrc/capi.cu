@@ -104,6 +104,7 @@ struct zvdb_index {
     bool descent = false;           // off = the reference's search (entry_point, layer 0 only)
     uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap, 3 global hash
     bool legacy_exchange = false;   // sharded step as three launches (search with peer stores, flag kernel, merge kernel) instead of one
+    bool exchange_blocks = false;   // fused step through result blocks + per-query release flags instead of 128-byte self-validating records
     bool stage_host_buffers = false; // zvdb_search_batch: always copy through device staging buffers (variant bit 11; A/B against zero-copy)
     uint32_t prefetch_mode = 0;     // K1 L2 prefetch: 0 automatic, else 1 + bits (bit 0 rows of a pop's later batches, bit 1 adjacency rows of evaluated neighbours)
     uint32_t bf_mode = 0;           // K4: 0 automatic (CTA pairs), 1 single CTAs, 2 CTA pairs
@@ -298,6 +299,10 @@ struct FusedExchange {
     uint64_t block_bytes;
     uint64_t *m_ids; float *m_dist; uint32_t *m_counts;
     uint32_t world, rank, epoch;
+    // record form (128-byte self-validating lines): ll_lines > 0
+    uint8_t *peer_ll[8] = {};
+    const uint8_t *ll_local = nullptr;
+    uint32_t ll_lines = 0, ll_pitch = 0, ll_nq = 0;
     // gather-to-owner (zvdb_search_batch_exchange_host): q_per > 0
     uint32_t q_per = 0;
     const float *peer_q[8] = {};
@@ -354,7 +359,7 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
         const uint64_t total = static_cast<uint64_t>(fx->world) * k;
         if (total > 4096) return fail(ZVDB_ERR_UNSUPPORTED, "merge: G*k > 4096");
         p.merge_p2 = next_pow2(static_cast<uint32_t>(total));
-        merge_smem = (static_cast<uint64_t>(p.merge_p2) + total) * 8;
+        merge_smem = (total * 12 + 8 * 4 + 15) & ~15ull;     // global ids u64 + distance words u32 per candidate, 8 list lengths
     }
     auto ctas_for = [](uint64_t smem) { return std::min<uint64_t>(32, (227ull * 1024) / (smem + 1024)); };
     const int vis = plan_visited(ix, ef);
@@ -421,6 +426,8 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
         p.qflags = fx->qflags; p.gather = fx->gather; p.block_bytes = fx->block_bytes;
         p.m_ids = fx->m_ids; p.m_dist = fx->m_dist; p.m_counts = fx->m_counts;
         p.ex_world = fx->world; p.ex_rank = fx->rank; p.ex_epoch = fx->epoch;
+        p.ll_local = fx->ll_local; p.ll_lines = fx->ll_lines; p.ll_pitch = fx->ll_pitch; p.ll_nq = fx->ll_nq;
+        for (uint32_t i = 0; i < fx->world; ++i) p.peer_ll[i] = fx->peer_ll[i];
         p.q_per = fx->q_per; p.sflags = fx->sflags; p.sflag_pitch = fx->sflag_pitch;
         for (uint32_t i = 0; i < fx->world; ++i) { p.peer_q[i] = fx->peer_q[i]; p.peer_sflags[i] = fx->peer_sflags[i]; }
         if (vis == kVisSmemHash) {                        // CTA b searches query b and merges query b - lag, one wave behind
@@ -1401,10 +1408,10 @@ int zvdb_sync_device(zvdb_index *ix) {
 int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
     const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u, bfm = (variant >> 4) & 3u;
-    if (width > 2 || bfm > 2 || variant > 8191 || ((variant >> 8) & 7u) > 4)
-        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = accepted and ignored (round 1's load-width variants are gone: never faster in any automatically chosen mode), bits 2-3 = visited set 0 auto/1 shared-memory hash/2 global bitmap/3 global hash, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-10 = L2 prefetch 0 auto/1 off/2 rows/3 adjacency/4 both, bit 11 = stage page-locked host buffers through device copies, bit 12 = sharded step as three launches (search, flag, merge) instead of the fused one");
+    if (width > 2 || bfm > 2 || variant > 16383 || ((variant >> 8) & 7u) > 4)
+        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = accepted and ignored (round 1's load-width variants are gone: never faster in any automatically chosen mode), bits 2-3 = visited set 0 auto/1 shared-memory hash/2 global bitmap/3 global hash, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-10 = L2 prefetch 0 auto/1 off/2 rows/3 adjacency/4 both, bit 11 = stage page-locked host buffers through device copies, bit 12 = sharded step as three launches (search, flag, merge) instead of the fused one, bit 13 = fused step through result blocks + release flags instead of 128-byte records");
     std::lock_guard<std::mutex> lk(ix->mu);
-    ix->prefetch_mode = (variant >> 8) & 7u; ix->stage_host_buffers = (variant >> 11) & 1u; ix->legacy_exchange = (variant >> 12) & 1u;
+    ix->prefetch_mode = (variant >> 8) & 7u; ix->stage_host_buffers = (variant >> 11) & 1u; ix->legacy_exchange = (variant >> 12) & 1u; ix->exchange_blocks = (variant >> 13) & 1u;
     ix->visited_mode = vis; ix->bf_mode = bfm; ix->bf_filter = (variant >> 6) & 1u; ix->bf_epilogue = (variant >> 7) & 1u;
     return ZVDB_OK;
 }
@@ -1675,6 +1682,8 @@ struct zvdb_exchange {
     uint32_t **d_peer_flags = nullptr;   // device array of world pointers
     uint64_t qflags_off = 0;         // per-query flag rows [nq_max][8] u32 (fused step): slot r of row q = last epoch rank r published for q
     uint64_t nq_max = 0;
+    uint64_t ll_off = 0;             // fused step, record form: [2][world][nq_max][ll_pitch] lines of 128 bytes
+    uint32_t ll_pitch = 0;           // lines reserved per record: ceil((2 * k_max + 1) / 30)
     uint64_t qbuf_off = 0;           // host step: [2][nq_max][dim_max] f32, this rank's slice of the query batch (by epoch parity)
     uint32_t dim_max = 0;
     uint64_t *d_out_ids = nullptr; float *d_out_dist = nullptr; uint32_t *d_out_counts = nullptr;   // host step with pageable result buffers: staging
@@ -1701,7 +1710,9 @@ int zvdb_exchange_create_host(zvdb_exchange **out, int device, uint32_t world, u
     ex->flags_off = 2 * ex->cap_bytes;
     ex->qflags_off = ex->flags_off + static_cast<size_t>(8) * kFlagPitch * sizeof(uint32_t);
     ex->nq_max = nq_max;
-    ex->qbuf_off = (ex->qflags_off + static_cast<size_t>(nq_max) * 8 * sizeof(uint32_t) + 255) / 256 * 256;
+    ex->ll_off = (ex->qflags_off + static_cast<size_t>(nq_max) * 8 * sizeof(uint32_t) + 255) / 256 * 256;
+    ex->ll_pitch = (2 * k_max + 1 + 29) / 30;
+    ex->qbuf_off = ex->ll_off + 2 * static_cast<size_t>(world) * nq_max * ex->ll_pitch * 128;
     ex->dim_max = dim_max;
     const size_t total = ex->qbuf_off + 2 * static_cast<size_t>(nq_max) * dim_max * sizeof(float);
     cudaError_t e = cudaMalloc(&ex->local, total);
@@ -1776,7 +1787,8 @@ int zvdb_search_batch_exchange(zvdb_index *ix, zvdb_exchange *ex, const float *d
         int rc = sync_device_locked(ix);
         if (rc) return rc;
     }
-    if (!ix->legacy_exchange && nq <= ex->nq_max) {
+    const bool records = !ix->exchange_blocks;
+    if (!ix->legacy_exchange && nq <= ex->nq_max && (!records || (2 * k + 1 + 29) / 30 <= ex->ll_pitch)) {
         // ONE launch: search, peer stores, per-query flags, and -- one wave behind -- the merge of every query whose
         // flag row is complete (an empty shard runs the same kernel and publishes zero results per query)
         FusedExchange fx{};
@@ -1785,6 +1797,11 @@ int zvdb_search_batch_exchange(zvdb_index *ix, zvdb_exchange *ex, const float *d
         fx.gather = ex->local + half; fx.block_bytes = block;
         fx.m_ids = out_ids; fx.m_dist = out_dist; fx.m_counts = out_counts;
         fx.world = ex->world; fx.rank = ex->rank; fx.epoch = epoch;
+        if (!ix->exchange_blocks) {
+            const uint64_t llhalf = ex->ll_off + (epoch & 1) * static_cast<uint64_t>(ex->world) * ex->nq_max * ex->ll_pitch * 128;
+            for (uint32_t g = 0; g < ex->world; ++g) fx.peer_ll[g] = ex->peer[g] + llhalf;
+            fx.ll_local = ex->local + llhalf; fx.ll_lines = (2 * k + 1 + 29) / 30; fx.ll_pitch = ex->ll_pitch; fx.ll_nq = static_cast<uint32_t>(ex->nq_max);
+        }
         return launch_search(ix, d_queries, nq, k, ef, nullptr, nullptr, nullptr, nullptr, nullptr, ex->world, ex->rank, s, blocks, ex->world, &fx);
     }
     if (empty) {
@@ -1815,6 +1832,8 @@ int zvdb_search_batch_exchange_host(zvdb_index *ix, zvdb_exchange *ex, const flo
     if (ef < k) return fail(ZVDB_ERR_INVALID, "search: ef must be >= k");
     if (dim == 0 || dim > ex->dim_max || nq > ex->nq_max)
         return fail(ZVDB_ERR_INVALID, "exchange: created without a query buffer for this dim / batch size (zvdb_exchange_create_host)");
+    if (!ix->exchange_blocks && (2 * k + 1 + 29) / 30 > ex->ll_pitch)
+        return fail(ZVDB_ERR_INVALID, "exchange: k exceeds the k_max the exchange was created with");
     const uint64_t block = zvdb_shard_block_bytes(nq, k);
     if (block * ex->world > ex->cap_bytes) return fail(ZVDB_ERR_INVALID, "exchange: nq * k exceeds the capacity the exchange was created with");
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -1871,6 +1890,11 @@ int zvdb_search_batch_exchange_host(zvdb_index *ix, zvdb_exchange *ex, const flo
     fx.gather = ex->local + half; fx.block_bytes = block;
     fx.m_ids = static_cast<uint64_t *>(di); fx.m_dist = static_cast<float *>(dd); fx.m_counts = static_cast<uint32_t *>(dc);
     fx.world = ex->world; fx.rank = ex->rank; fx.epoch = epoch; fx.q_per = static_cast<uint32_t>(per);
+    if (!ix->exchange_blocks) {
+        const uint64_t llhalf = ex->ll_off + (epoch & 1) * static_cast<uint64_t>(ex->world) * ex->nq_max * ex->ll_pitch * 128;
+        for (uint32_t g = 0; g < ex->world; ++g) fx.peer_ll[g] = ex->peer[g] + llhalf;
+        fx.ll_local = ex->local + llhalf; fx.ll_lines = (2 * k + 1 + 29) / 30; fx.ll_pitch = ex->ll_pitch; fx.ll_nq = static_cast<uint32_t>(ex->nq_max);
+    }
     int rc = launch_search(ix, nullptr, nq, k, ef, nullptr, nullptr, nullptr, nullptr, nullptr, ex->world, ex->rank, s, blocks, ex->world, &fx);
     if (rc) return rc;
     if (!direct && hi > lo) {

@@ -94,6 +94,17 @@ struct SearchParams {
     // a warp reads its query from the owner's memory over NVLink (after the owner's kernel has announced that its
     // slice landed: slice flag), sends its shard's top-k to the owner only, and only the owner merges the query.
     // Every query and every result crosses PCIe once, and the exchange moves 1/ex_world of the all-gather's bytes.
+    // Record form of the fused exchange (default; ll_lines > 0). A shard's top-k for one query travels as ll_lines
+    // self-validating 128-byte lines: 30 payload words (k local ids u32, k distances f32, the count) + 2 flag words
+    // holding ex_epoch, written by ONE warp-wide 4-byte-per-lane store per line and receiver -- 128-byte stores of a
+    // warp land atomically over NVLink (the property NCCL's LL128 protocol is built on), so the receiver polls the
+    // line itself: no separate flag store, no release fence, and 1 NVLink request per (query, receiver) at k <= 14
+    // instead of ~6 sector writes + a flag. Slot of (sender s, query q): ((s * ll_nq + q) * ll_pitch) lines.
+    uint8_t *peer_ll[8];         // peer g's record buffer (this epoch's parity half), mapped
+    const uint8_t *ll_local;     // this rank's own record buffer (same half)
+    uint32_t ll_lines;           // lines a record of k results needs: ceil((2k + 1) / 30); 0 = block form
+    uint32_t ll_pitch;           // lines reserved per record (from k_max: fixed per exchange, so flag words stay flag words)
+    uint32_t ll_nq;              // queries reserved per sender (nq_max)
     uint32_t q_per;
     const float *peer_q[8];      // rank o's query buffer [nq][dim] (rows of slice o valid), mapped
     uint32_t *peer_sflags[8];    // peer g's slice flags [8] x pitch: slot r = last epoch whose slice r is in place
@@ -428,12 +439,53 @@ struct MergeLess {
 
 // Fused exchange, receiving side: one warp merges query q of this step from the LOCAL gather buffer (filled by every
 // rank's search epilogue through its peer mapping) once all ex_world ranks have published ex_epoch for q.
-__device__ __forceinline__ void merge_one_query(const SearchParams &p, uint32_t q, uint64_t *keys, uint32_t lane) {
+// The ex_world shard lists arrive sorted by (distance, global id) (the search epilogue re-orders exact distance ties
+// by id in peer mode), so the merge is a k-step tournament over the list heads: lane g owns list g, every step takes
+// the warp minimum of the heads by two/three 32-bit REDUX passes (distance word, then the 64-bit global id) and the
+// winner advances. ~25 instructions per output instead of a bitonic sort of all ex_world * k candidates
+// (1 500-2 000 instructions per query at 8 x 10: as much as a 10-pop search itself).
+__device__ __noinline__ void merge_one_query(const SearchParams &p, uint32_t q, uint64_t *scratch, uint32_t lane) {
+    const uint32_t k = p.k, total = p.ex_world * k;
+    uint64_t *gid = scratch;                                         // [total] global ids, list g at [g*k, g*k + k)
+    uint32_t *dord = reinterpret_cast<uint32_t *>(scratch + total);  // [total] ordered distance words
+    uint32_t cnt = 0, head = 0;                                      // lane g < ex_world: list g's length and cursor
+    if (p.ll_lines) {
+        // Record form: read every sender's lines (one warp-wide 128-byte load each, all senders' first lines in flight
+        // together), retry until the flag words of all of them show this epoch, then unpack into the merge scratch.
+        const size_t rec_bytes = static_cast<size_t>(p.ll_pitch) * 128;
+        for (uint32_t L = 0; L < p.ll_lines; ++L) {
+            uint32_t v[8];
+            for (uint32_t spins = 0;; ++spins) {
+                bool ok = true;
+#pragma unroll
+                for (uint32_t g = 0; g < 8; ++g) {
+                    v[g] = p.ex_epoch;
+                    if (g < p.ex_world) {
+                        const uint8_t *line = p.ll_local + (static_cast<size_t>(g) * p.ll_nq + q) * rec_bytes + L * 128 + lane * 4;
+                        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v[g]) : "l"(line) : "memory");
+                    }
+                }
+#pragma unroll
+                for (uint32_t g = 0; g < 8; ++g) ok = ok && (lane < 30 || v[g] == p.ex_epoch);
+                if (__all_sync(kFullMask, ok)) break;
+                if (spins > 8) __nanosleep(spins > 64 ? 1000 : 100);
+            }
+            const uint32_t w = L * 30 + lane;                        // payload word this lane holds (lanes 30, 31: flags)
+#pragma unroll
+            for (uint32_t g = 0; g < 8; ++g) {
+                if (g < p.ex_world && lane < 30) {
+                    if (w < k) gid[g * k + w] = static_cast<uint64_t>(v[g]) * p.ex_world + g;
+                    else if (w < 2 * k) dord[g * k + (w - k)] = float_to_ordered(__uint_as_float(v[g]));
+                    else if (w == 2 * k) reinterpret_cast<uint32_t *>(dord + total)[g] = v[g];     // counts behind the distances
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < p.ex_world) cnt = min(reinterpret_cast<uint32_t *>(dord + total)[lane], k);
+    } else {
     {
         // Warp-uniform wait: every lane polls (lanes past ex_world re-read the last rank's flag) and the loop exits on a
-        // warp vote, so control flow never diverges. A divergent spin loop here made the compiler treat the whole
-        // persistent query loop as possibly diverged and wrap every shuffle / vote of the pop loop in WARPSYNC +
-        // collective bookkeeping: +12 % executed instructions, +10 % time on the L2-resident reference graph (round 2).
+        // warp vote, so control flow never diverges.
         const uint32_t *f = p.qflags + static_cast<size_t>(q) * 8 + min(lane, p.ex_world - 1u);
         for (uint32_t spins = 0;; ++spins) {
             uint32_t v;
@@ -442,33 +494,36 @@ __device__ __forceinline__ void merge_one_query(const SearchParams &p, uint32_t 
             if (spins > 8) __nanosleep(spins > 64 ? 1000 : 100);
         }
     }
-    const uint32_t k = p.k, total = p.ex_world * k, p2 = p.merge_p2;
-    uint64_t *gid = keys + p2;
     const size_t nk = static_cast<size_t>(p.nq) * k;
-    uint32_t valid = 0;
-    for (uint32_t i = lane; i < p2; i += 32) {
-        uint64_t key = ~0ull;
-        if (i < total) {
-            const uint32_t gsh = i / k, j = i - gsh * k;
-            const uint8_t *blk = p.gather + gsh * p.block_bytes;
-            const size_t src = static_cast<size_t>(q) * k + j;
-            gid[i] = __ldcg(reinterpret_cast<const uint64_t *>(blk) + src);          // L2: the bytes came in over NVLink
-            const uint32_t cnt = __ldcg(reinterpret_cast<const uint32_t *>(blk + nk * 12) + q);
-            if (j < cnt) {
-                key = (static_cast<uint64_t>(float_to_ordered(__ldcg(reinterpret_cast<const float *>(blk + nk * 8) + src))) << 32) | i;
-                ++valid;
-            }
-        }
-        keys[i] = key;
+    for (uint32_t i = lane; i < total; i += 32) {
+        const uint32_t gsh = i / k, j = i - gsh * k;
+        const uint8_t *blk = p.gather + gsh * p.block_bytes;
+        const size_t src = static_cast<size_t>(q) * k + j;
+        gid[i] = __ldcg(reinterpret_cast<const uint64_t *>(blk) + src);              // L2: the bytes came in over NVLink
+        dord[i] = float_to_ordered(__ldcg(reinterpret_cast<const float *>(blk + nk * 8) + src));
     }
-    bitonic_sort_u64(keys, p2, MergeLess{gid});
-    valid = __reduce_add_sync(kFullMask, valid);
-    const uint32_t nres = min(valid, k);
-    for (uint32_t r = lane; r < k; r += 32) {
+    if (lane < p.ex_world) cnt = min(__ldcg(reinterpret_cast<const uint32_t *>(p.gather + lane * p.block_bytes + nk * 12) + q), k);
+    }
+    const uint32_t nres = min(__reduce_add_sync(kFullMask, cnt), k);
+    __syncwarp();
+    for (uint32_t r = 0; r < k; ++r) {
         const size_t o = static_cast<size_t>(q) * k + r;
-        uint64_t oid = ~0ull; float od = 0.0f;
-        if (r < nres) { const uint64_t key = keys[r]; oid = gid[static_cast<uint32_t>(key)]; od = ordered_to_float(static_cast<uint32_t>(key >> 32)); }
-        p.m_ids[o] = oid; p.m_dist[o] = od;
+        if (r >= nres) {                                             // (uniform) fewer than k candidates in all shards together
+            if (lane == 0) { p.m_ids[o] = ~0ull; p.m_dist[o] = 0.0f; }
+            continue;
+        }
+        const bool alive = head < cnt;                               // some lane is alive: r < nres
+        const uint32_t slot = min(lane, p.ex_world - 1u) * k + min(head, k - 1u);
+        const uint32_t d = alive ? dord[slot] : 0xFFFFFFFFu;
+        const uint64_t g = gid[slot];
+        const uint32_t dmin = __reduce_min_sync(kFullMask, d);
+        bool in = alive && d == dmin;
+        const uint32_t ghi = __reduce_min_sync(kFullMask, in ? static_cast<uint32_t>(g >> 32) : 0xFFFFFFFFu);
+        in = in && static_cast<uint32_t>(g >> 32) == ghi;
+        const uint32_t glo = __reduce_min_sync(kFullMask, in ? static_cast<uint32_t>(g) : 0xFFFFFFFFu);
+        in = in && static_cast<uint32_t>(g) == glo;
+        const uint32_t w = __ffs(__ballot_sync(kFullMask, in)) - 1;  // global ids are distinct: exactly one lane (guard: the first)
+        if (lane == w) { p.m_ids[o] = g; p.m_dist[o] = ordered_to_float(d); ++head; }
     }
     if (lane == 0) p.m_counts[q] = nres;
     __syncwarp();
@@ -486,7 +541,7 @@ __device__ __forceinline__ void merge_one_query(const SearchParams &p, uint32_t 
 // In the global modes the CTA is persistent and owns one table.
 template <int CPL, int METRIC, int VIS>
 __global__ void __launch_bounds__(32, (CPL <= 2 ? 32 : 16))
-search_layer0_kernel(const SearchParams p) {
+search_layer0_kernel(const __grid_constant__ SearchParams p) {
     constexpr int U = Unroll<CPL, false>::value;
     constexpr uint32_t LPR = 32 / U;                            // lanes holding the same row after the reduce
     constexpr bool GLOBAL_VIS = VIS != kVisSmemHash;
@@ -753,11 +808,42 @@ search_layer0_kernel(const SearchParams p) {
     const uint32_t nres = min(np, p.k);
     // receivers of this query's shard-local top-k: every rank (all-gather), or only the query's owner
     const uint32_t g_lo = p.q_per ? q / p.q_per : 0u, g_hi = p.q_per ? g_lo + 1u : p.n_peers;
+    if (p.ex_world) {
+        // Fused exchange: the receivers merge by a tournament over list heads, which needs each shard list in the
+        // merge's own total order (distance, id). The list is the SAME k entries as the plain result (the first k of the
+        // stable sort above -- the oracle's per-shard definition); only exact distance ties among them change places.
+        const uint32_t kp2 = next_pow2(p.k);                         // <= next_pow2(ef) <= cand_cap
+        for (uint32_t r = lane; r < kp2; r += 32)                    // in place: slot r is read and written by its own lane only
+            sorted[r] = r < nres ? *res_at(static_cast<uint32_t>(sorted[r])) : ~0ull;
+        bitonic_sort_u64(sorted, kp2);
+    }
+    if (p.ll_lines) {
+        // Record form: line L = payload words [30 L, 30 L + 30) of (k local ids | k distance bits | count) + the epoch
+        // twice; one warp-wide store per line and receiver.
+        __syncwarp();
+        const size_t rec = (static_cast<size_t>(p.ex_rank) * p.ll_nq + q) * (static_cast<size_t>(p.ll_pitch) * 128) + lane * 4;
+        for (uint32_t L = 0; L < p.ll_lines; ++L) {
+            const uint32_t w = L * 30 + lane;
+            uint32_t v = p.ex_epoch;                                 // lanes 30, 31
+            if (lane < 30) {
+                v = 0u;
+                if (w < p.k) v = w < nres ? key_id(sorted[w]) : kInvalidId;
+                else if (w < 2 * p.k) v = (w - p.k) < nres ? __float_as_uint(key_dist(sorted[w - p.k])) : 0u;
+                else if (w == 2 * p.k) v = nres;
+            }
+            for (uint32_t g = g_lo; g < g_hi; ++g)
+                asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p.peer_ll[g] + rec + L * 128), "r"(v) : "memory");
+        }
+        if (lane == 0) {
+            if (p.pops) p.pops[q] = np;
+            if (p.evals) p.evals[q] = nev + (p.seeds ? __ldg(p.seeds + q).z : 0u);
+        }
+    } else {
     for (uint32_t r = lane; r < p.k; r += 32) {
         const size_t o = static_cast<size_t>(q) * p.k + r;
         uint64_t oid = ~0ull; float od = 0.0f;
         if (r < nres) {
-            const uint64_t key = *res_at(static_cast<uint32_t>(sorted[r]));
+            const uint64_t key = p.ex_world ? sorted[r] : *res_at(static_cast<uint32_t>(sorted[r]));
             oid = static_cast<uint64_t>(key_id(key)) * p.id_stride + p.id_base;
             od = key_dist(key);
         }
@@ -785,6 +871,7 @@ search_layer0_kernel(const SearchParams p) {
         if (lane >= g_lo && lane < g_hi)
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_qflags[lane] + static_cast<size_t>(q) * 8 + p.ex_rank), "r"(p.ex_epoch) : "memory");
     }
+    }   // block form
     if (VIS == kVisGlobalBitmap) {       // wipe exactly the words this query set
         __syncwarp();
         const uint32_t nev4 = nev & ~3u;                 // the log is 16-byte aligned: four ids per load

@@ -8,9 +8,12 @@ per-shard top-k are then exchanged once and merged by (distance, global id):
 
   * ``exchange="p2p"``  (default on CUDA): ONE kernel launch per step. The search kernel's epilogue
     stores each shard's top-k straight into every peer's gather buffer over NVLink (CUDA IPC
-    mappings) and publishes a per-query flag in every peer; one wave later the same kernel merges
-    each query whose flags are complete -- no collective call, no second launch
+    mappings) as 128-byte self-validating records (payload + epoch in one warp-wide store, atomic
+    over NVLink: no flag store, no fence); one wave later the same kernel merges each query whose
+    records have all arrived -- no collective call, no second launch
     (zvdb_search_batch_exchange);
+  * ``exchange="p2pb"``: the same one-launch step with the results travelling as per-rank blocks plus
+    per-query release flags instead of self-validating 128-byte records (the first fused form, A/B);
   * ``exchange="p2p3"``: round 1's form of the same exchange as three launches (search with peer
     stores, a flag kernel, a merge kernel that waits on the flags), kept for A/B;
   * ``exchange="nccl"``: search into a packed block, ONE ``all_gather_into_tensor`` of the blocks,
@@ -155,8 +158,8 @@ class ShardedHNSW:
         self.group = group
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
-        if exchange not in ("p2p", "p2p3", "nccl"):
-            raise ValueError("exchange must be 'p2p', 'p2p3' or 'nccl'")
+        if exchange not in ("p2p", "p2pb", "p2p3", "nccl"):
+            raise ValueError("exchange must be 'p2p', 'p2pb', 'p2p3' or 'nccl'")
         self.exchange = exchange
         self.m = m
         self.n_total = 0
@@ -164,6 +167,8 @@ class ShardedHNSW:
             self.index = HNSW(m, ef_construction, metric=metric, device=self.rank if device is None else device)
             if exchange == "p2p3":
                 self.index.set_kernel_variant(0x1000)          # bit 12: the sharded step as three launches
+            if exchange == "p2pb":
+                self.index.set_kernel_variant(0x2000)          # bit 13: fused step through result blocks + release flags
             self.backend = CudaBackend(self.index, self.rank, self.world)
         else:
             self.index = None
@@ -201,7 +206,7 @@ class ShardedHNSW:
         import torch.distributed as dist
         ef = ef or k
         e = ef_per_shard if ef_per_shard is not None else per_shard_ef(ef, k, self.world)
-        if self.exchange in ("p2p", "p2p3") and hasattr(self.backend, "search_exchange"):
+        if self.exchange in ("p2p", "p2pb", "p2p3") and hasattr(self.backend, "search_exchange"):
             self.ensure_exchange(nq, k)
             return self.backend.search_exchange(d_queries, nq, k, e)
         block = self.backend.search_packed(d_queries, nq, k, e)

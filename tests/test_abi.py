@@ -112,9 +112,9 @@ int main(void) {
 def test_search_kernels_fit_their_register_budget_without_spills(zv):
     """Every instantiation of the hot-path kernel must fit the register budget its residency needs (one-warp CTAs:
     32 per SM -> 64 registers for rows up to 1 KiB) without spills in the pop loop: a spill there cost 12-19 % when
-    it was measured (profiles/r01_k1_experiments.md), so it must not come back unnoticed. Every shared-memory-hash
-    instantiation (the mode of every default bench line) and the 128-d L2 bitmap one (C2's large-ef mode) have no stack
-    frame at all; the other global-visited ones (256-d rows, cosine / dot, the hash fallback for > 14.5 M-row shards)
+    it was measured (profiles/r01_k1_experiments.md), so it must not come back unnoticed. Of the plain-search
+    instantiations (EXCH = false) every shared-memory-hash one (the mode of every default bench line) and the 128-d L2
+    bitmap one (C2's large-ef mode) have no stack frame at all; the sharded-step instantiations and the other global-visited ones (256-d rows, cosine / dot, the hash fallback for > 14.5 M-row shards)
     keep one 4-byte value (the lane id) on the stack, re-read only in the per-query epilogue (checked in the SASS when it
     appeared, round 2) -- 8 bytes of stack are tolerated there and nowhere else."""
     import re
@@ -124,12 +124,12 @@ def test_search_kernels_fit_their_register_budget_without_spills(zv):
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     out = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
     rows = re.findall(r"Function (\S*search_layer0_kernel\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
-    assert len(rows) >= 45, "search_layer0_kernel instantiations not found in the library"
+    assert len(rows) >= 90, "search_layer0_kernel instantiations not found in the library"
     for name, reg, stack in rows:
-        m = re.search(r"search_layer0_kernelILi(\d+)ELi(\d)ELi(\d)E", name)       # <CPL, METRIC, VIS>
+        m = re.search(r"search_layer0_kernelILi(\d+)ELi(\d)ELi(\d)ELb([01])E", name)       # <CPL, METRIC, VIS, EXCH>
         assert m, name
-        cpl, metric, vis = int(m.group(1)), int(m.group(2)), int(m.group(3))
-        allowed = 0 if (vis == 0 or (cpl == 1 and metric == 0 and vis == 1)) else 8
+        cpl, metric, vis, exch = int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4))
+        allowed = 0 if (not exch and (vis == 0 or (cpl == 1 and metric == 0 and vis == 1))) else 8
         assert int(stack) <= allowed, f"{name} spills ({stack} bytes of stack)"
         if cpl <= 2:
             assert int(reg) <= 64, f"{name}: {reg} registers, 32 one-warp CTAs per SM need <= 64"

@@ -216,9 +216,9 @@ static int sync_upper_locked(zvdb_index *ix) {
 
 // ---- K1 launch ------------------------------------------------------------------------------
 
-template <int CPL, int METRIC, int VIS>
+template <int CPL, int METRIC, int VIS, bool EXCH>
 static cudaError_t launch_search_inst(const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
-    auto kern = search_layer0_kernel<CPL, METRIC, VIS>;
+    auto kern = search_layer0_kernel<CPL, METRIC, VIS, EXCH>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
@@ -227,25 +227,31 @@ static cudaError_t launch_search_inst(const SearchParams &p, unsigned grid, size
     return cudaGetLastError();
 }
 
-template <int METRIC, int VIS>
+template <int METRIC, int VIS, bool EXCH>
 static cudaError_t launch_search_metric(int cpl, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     switch (cpl) {
-        case 1: return launch_search_inst<1, METRIC, VIS>(p, grid, smem, s);
-        case 2: return launch_search_inst<2, METRIC, VIS>(p, grid, smem, s);
-        case 4: return launch_search_inst<4, METRIC, VIS>(p, grid, smem, s);
-        case 6: return launch_search_inst<6, METRIC, VIS>(p, grid, smem, s);
-        case 8: return launch_search_inst<8, METRIC, VIS>(p, grid, smem, s);
+        case 1: return launch_search_inst<1, METRIC, VIS, EXCH>(p, grid, smem, s);
+        case 2: return launch_search_inst<2, METRIC, VIS, EXCH>(p, grid, smem, s);
+        case 4: return launch_search_inst<4, METRIC, VIS, EXCH>(p, grid, smem, s);
+        case 6: return launch_search_inst<6, METRIC, VIS, EXCH>(p, grid, smem, s);
+        case 8: return launch_search_inst<8, METRIC, VIS, EXCH>(p, grid, smem, s);
     }
     return cudaErrorInvalidValue;
 }
 
-template <int VIS>
-static cudaError_t launch_search_vis(int metric, int cpl, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+template <int VIS, bool EXCH>
+static cudaError_t launch_search_vis2(int metric, int cpl, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     switch (metric) {
-        case 0: return launch_search_metric<kMetricL2, VIS>(cpl, p, grid, smem, s);
-        case 1: return launch_search_metric<kMetricCos, VIS>(cpl, p, grid, smem, s);
-        default: return launch_search_metric<kMetricDot, VIS>(cpl, p, grid, smem, s);
+        case 0: return launch_search_metric<kMetricL2, VIS, EXCH>(cpl, p, grid, smem, s);
+        case 1: return launch_search_metric<kMetricCos, VIS, EXCH>(cpl, p, grid, smem, s);
+        default: return launch_search_metric<kMetricDot, VIS, EXCH>(cpl, p, grid, smem, s);
     }
+}
+
+// exch = any sharded form of the step (peer stores, records, flags, merge tail): its own instantiation, see the kernel
+template <int VIS>
+static cudaError_t launch_search_vis(bool exch, int metric, int cpl, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    return exch ? launch_search_vis2<VIS, true>(metric, cpl, p, grid, smem, s) : launch_search_vis2<VIS, false>(metric, cpl, p, grid, smem, s);
 }
 
 template <int METRIC>
@@ -443,9 +449,10 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
         ix->launches++;
         ZV_CUDA(e);
     }
-    if (vis == kVisSmemHash) e = launch_search_vis<kVisSmemHash>(g.metric, cpl, p, grid, smem, s);
-    else if (vis == kVisGlobalBitmap) e = launch_search_vis<kVisGlobalBitmap>(g.metric, cpl, p, grid, smem, s);
-    else e = launch_search_vis<kVisGlobalHash>(g.metric, cpl, p, grid, smem, s);
+    const bool exch = n_peers != 0 || fx != nullptr;
+    if (vis == kVisSmemHash) e = launch_search_vis<kVisSmemHash>(exch, g.metric, cpl, p, grid, smem, s);
+    else if (vis == kVisGlobalBitmap) e = launch_search_vis<kVisGlobalBitmap>(exch, g.metric, cpl, p, grid, smem, s);
+    else e = launch_search_vis<kVisGlobalHash>(exch, g.metric, cpl, p, grid, smem, s);
     ix->launches++;
     ZV_CUDA(e);
     if (vis != kVisSmemHash || p.seeds) ZV_CUDA(cudaEventRecord(ix->bitmap_ev, s));

@@ -539,12 +539,16 @@ __device__ __noinline__ void merge_one_query(const SearchParams &p, uint32_t q, 
 //                    probe), n/8 bytes per resident CTA, wiped from a log of the set ids (round 1's large-ef path,
 //                    kept as an A/B variant).
 // In the global modes the CTA is persistent and owns one table.
-template <int CPL, int METRIC, int VIS>
+// EXCH = the sharded forms of the step (peer stores, records, flags, the merge tail). The plain search is a separate
+// instantiation with none of that code in it: in round 2 every piece of exchange code added behind a run-time test still
+// cost the global-visited modes 8-10 % (the 64-register pop loop is allocated together with whatever surrounds it).
+template <int CPL, int METRIC, int VIS, bool EXCH>
 __global__ void __launch_bounds__(32, (CPL <= 2 ? 32 : 16))
 search_layer0_kernel(const __grid_constant__ SearchParams p) {
     constexpr int U = Unroll<CPL, false>::value;
     constexpr uint32_t LPR = 32 / U;                            // lanes holding the same row after the reduce
     constexpr bool GLOBAL_VIS = VIS != kVisSmemHash;
+    const uint32_t x_world = EXCH ? p.ex_world : 0u, x_qper = EXCH ? p.q_per : 0u, x_lines = EXCH ? p.ll_lines : 0u, x_peers = EXCH ? p.n_peers : 0u;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // Two layouts of the same arrays (same total). Global modes: the fixed-size scratch first, at compile-time offsets
     // (no address arithmetic on the hot path; measured +7..16 % at ef >= 128). Shared-hash mode keeps the lists first:
@@ -591,7 +595,7 @@ search_layer0_kernel(const __grid_constant__ SearchParams p) {
     const uint32_t lane = threadIdx.x;
     const float4 *__restrict__ arena = p.arena;
     const uint32_t pass_w = min(p.m, 32u);
-    if (p.q_per && blockIdx.x == 0 && lane < p.ex_world && lane != p.ex_rank)   // our slice of the queries is in place (copied before this launch)
+    if (x_qper && blockIdx.x == 0 && lane < x_world && lane != p.ex_rank)   // our slice of the queries is in place (copied before this launch)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_sflags[lane] + static_cast<size_t>(p.ex_rank) * p.sflag_pitch), "r"(p.ex_epoch) : "memory");
 
     for (uint32_t q = blockIdx.x;; q += gridDim.x) {            // persistent when gridDim.x < nq
@@ -599,8 +603,8 @@ search_layer0_kernel(const __grid_constant__ SearchParams p) {
     // Query -> registers, chunked like an arena row, packed in pairs for the f32x2 pipe.
     Chunk2 qv[CPL];
     const float *qsrc = p.queries;
-    if (p.q_per) {                                        // gather-to-owner: the query lives in its owner's HBM
-        const uint32_t owner = q / p.q_per;
+    if (x_qper) {                                        // gather-to-owner: the query lives in its owner's HBM
+        const uint32_t owner = q / x_qper;
         qsrc = p.peer_q[owner];
         if (owner != p.ex_rank) {                         // (our own slice was copied in before this kernel, stream order)
             const uint32_t *f = p.sflags + static_cast<size_t>(owner) * p.sflag_pitch;
@@ -807,8 +811,8 @@ search_layer0_kernel(const __grid_constant__ SearchParams p) {
     bitonic_sort_u64(sorted, p2);
     const uint32_t nres = min(np, p.k);
     // receivers of this query's shard-local top-k: every rank (all-gather), or only the query's owner
-    const uint32_t g_lo = p.q_per ? q / p.q_per : 0u, g_hi = p.q_per ? g_lo + 1u : p.n_peers;
-    if (p.ex_world) {
+    const uint32_t g_lo = x_qper ? q / x_qper : 0u, g_hi = x_qper ? g_lo + 1u : x_peers;
+    if (x_world) {
         // Fused exchange: the receivers merge by a tournament over list heads, which needs each shard list in the
         // merge's own total order (distance, id). The list is the SAME k entries as the plain result (the first k of the
         // stable sort above -- the oracle's per-shard definition); only exact distance ties among them change places.
@@ -817,12 +821,12 @@ search_layer0_kernel(const __grid_constant__ SearchParams p) {
             sorted[r] = r < nres ? *res_at(static_cast<uint32_t>(sorted[r])) : ~0ull;
         bitonic_sort_u64(sorted, kp2);
     }
-    if (p.ll_lines) {
+    if (x_lines) {
         // Record form: line L = payload words [30 L, 30 L + 30) of (k local ids | k distance bits | count) + the epoch
         // twice; one warp-wide store per line and receiver.
         __syncwarp();
         const size_t rec = (static_cast<size_t>(p.ex_rank) * p.ll_nq + q) * (static_cast<size_t>(p.ll_pitch) * 128) + lane * 4;
-        for (uint32_t L = 0; L < p.ll_lines; ++L) {
+        for (uint32_t L = 0; L < x_lines; ++L) {
             const uint32_t w = L * 30 + lane;
             uint32_t v = p.ex_epoch;                                 // lanes 30, 31
             if (lane < 30) {
@@ -843,11 +847,11 @@ search_layer0_kernel(const __grid_constant__ SearchParams p) {
         const size_t o = static_cast<size_t>(q) * p.k + r;
         uint64_t oid = ~0ull; float od = 0.0f;
         if (r < nres) {
-            const uint64_t key = p.ex_world ? sorted[r] : *res_at(static_cast<uint32_t>(sorted[r]));
+            const uint64_t key = x_world ? sorted[r] : *res_at(static_cast<uint32_t>(sorted[r]));
             oid = static_cast<uint64_t>(key_id(key)) * p.id_stride + p.id_base;
             od = key_dist(key);
         }
-        if (p.n_peers == 0) { p.ids[o] = oid; p.dist[o] = od; }
+        if (x_peers == 0) { p.ids[o] = oid; p.dist[o] = od; }
         else {
             const size_t nk = static_cast<size_t>(p.nq) * p.k;
             for (uint32_t g = g_lo; g < g_hi; ++g) {
@@ -857,7 +861,7 @@ search_layer0_kernel(const __grid_constant__ SearchParams p) {
         }
     }
     if (lane == 0) {
-        if (p.n_peers == 0) p.counts[q] = nres;
+        if (x_peers == 0) p.counts[q] = nres;
         else {
             const size_t nk = static_cast<size_t>(p.nq) * p.k;
             for (uint32_t g = g_lo; g < g_hi; ++g) reinterpret_cast<uint32_t *>(p.peer_blocks[g] + nk * 12)[q] = nres;
@@ -865,7 +869,7 @@ search_layer0_kernel(const __grid_constant__ SearchParams p) {
         if (p.pops) p.pops[q] = np;
         if (p.evals) p.evals[q] = nev + (p.seeds ? __ldg(p.seeds + q).z : 0u);
     }
-    if (p.ex_world) {
+    if (x_world) {
         // publish: every lane's peer stores above are ordered before the flag by the warp barrier + the release store
         __syncwarp();
         if (lane >= g_lo && lane < g_hi)
@@ -898,11 +902,11 @@ search_layer0_kernel(const __grid_constant__ SearchParams p) {
     __syncwarp();
     }   // q < nq
 
-    if (p.ex_world) {
+    if (x_world) {
         // fused merge, one wave behind the search: persistent grids merge the query this CTA searched one iteration
         // ago (q - gridDim.x), one-CTA-per-query grids the query merge_lag CTAs back (grid = nq + merge_lag)
         const uint32_t lag = GLOBAL_VIS ? gridDim.x : p.merge_lag;
-        if (q >= lag && q - lag < p.nq && (p.q_per == 0 || (q - lag) / p.q_per == p.ex_rank)) merge_one_query(p, q - lag, reinterpret_cast<uint64_t *>(smem_raw + p.merge_off), lane);
+        if (q >= lag && q - lag < p.nq && (x_qper == 0 || (q - lag) / x_qper == p.ex_rank)) merge_one_query(p, q - lag, reinterpret_cast<uint64_t *>(smem_raw + p.merge_off), lane);
     }
     if (q >= p.nq) break;
     }   // persistent query loop

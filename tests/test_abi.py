@@ -148,3 +148,25 @@ def test_library_sass_holds_the_blackwell_instructions_the_design_claims(zv):
                      "FFMA2", "REDUX", "CCTL.E.PF2"):
         assert mnemonic in sass, f"{mnemonic} not found in libzvdb_b200.so"
     assert "HMMA.16" not in sass and "WGMMA" not in sass     # no mma.sync / wgmma fallback kernels
+
+
+def test_c_benchmark_harness_compiles_and_refuses_without_a_gpu(zv, tmp_path):
+    """integration/harness.c (the reference's benchmark loops over the C ABI, for per-call numbers without the Python
+    interpreter) builds warning-free as C99 against the header and the library; without a GPU it fails loudly."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    libdir = os.path.join(ROOT, "zvdb_b200", "lib")
+    exe = tmp_path / "harness"
+    r = subprocess.run([cc, "-O2", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "integration", "harness.c"), "-o", str(exe), "-L", libdir, "-lzvdb_b200",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe), "200", "16", "50", "5"], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "Search per second" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 1 and "no CPU fallback" in run.stderr, run.stdout + run.stderr

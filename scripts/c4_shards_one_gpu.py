@@ -135,6 +135,8 @@ def main():
         z.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(z) / args.steps
+        step(0, e)                       # the checksum below is of batch 0, like bench.py's sweep lines (round 2's committed run took it
+        torch.cuda.synchronize()         # from the last timed step = batch 1, so its sums do not compare with the 8-GPU file's)
         line = {"metric": "batched search QPS (id-sharded index held by one GPU)", "value": nq / (ms * 1e-3), "unit": "queries/s",
                 "n_gpus": 1, "shards": S, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                 "config": {"workload": f"{args.rows}x{dim} fp32 L2 synthetic Gaussian, M={args.m}, {nq}-query batch, k={k}, ef={ef} "

@@ -104,6 +104,7 @@ struct zvdb_index {
     bool descent = false;           // off = the reference's search (entry_point, layer 0 only)
     uint32_t visited_mode = 0;      // 0 automatic, 1 shared-memory hash, 2 global bitmap, 3 global hash
     bool legacy_exchange = false;   // sharded step as three launches (search with peer stores, flag kernel, merge kernel) instead of one
+    bool bitmap_oom = false;        // the per-CTA visited bitmaps did not fit this device once: automatic mode uses the hash from then on
     bool exchange_blocks = false;   // fused step through result blocks + per-query release flags instead of 128-byte self-validating records
     bool stage_host_buffers = false; // zvdb_search_batch: always copy through device staging buffers (variant bit 11; A/B against zero-copy)
     uint32_t prefetch_mode = 0;     // K1 L2 prefetch: 0 automatic, else 1 + bits (bit 0 rows of a pop's later batches, bit 1 adjacency rows of evaluated neighbours)
@@ -285,12 +286,14 @@ static int plan_visited(const zvdb_index *ix, uint32_t ef) {
     const uint64_t ctas = std::min<uint64_t>(32, (227ull * 1024) / (smem_hash + 1024));
     // On chip while that still leaves >= 20 queries per SM. Beyond that, in global memory, per resident CTA: the n-bit
     // bitmap (one atomicOr per neighbour, never a second probe: the fastest form measured, profiles/r02_k1_visited_ab.jsonl)
-    // while the bitmaps of all resident CTAs fit an 8 GiB scratch budget (n <= 14.5 M rows at full residency: a 12.5 M-row
-    // C4 shard still qualifies, 7.4 GB next to 6.4 GB of rows on a 180 GB part); the hash table sized by ef * m (40 KB per
-    // CTA at ef = 512 whatever n is, but 15-45 % slower: probes past the first slot are extra L2 round trips on a pop's
-    // critical path) for larger shards, where n/8 bytes per CTA would cost tens of gigabytes.
+    // while the bitmaps of all resident CTAs fit a 32 GiB scratch budget (n <= 58 M rows at full residency: 7.4 GB next to
+    // 6.4 GB of rows on a 12.5 M-row C4 shard, 29.6 GB next to 25.6 GB on a 50 M-row one, on a 180 GB part) AND the
+    // allocation succeeds (an out-of-memory answer switches the handle to the hash for good); the hash table sized by
+    // ef * m (40 KB per CTA at ef = 512 whatever n is, but 15-45 % slower: probes past the first slot are extra L2 round
+    // trips on a pop's critical path) for larger shards and tighter devices.
     const uint64_t bitmap_bytes = (g.n + 31) / 32 * 4 * 32ull * static_cast<uint64_t>(ix->num_sms);
-    int vis = (smem_hash <= ix->smem_optin && ctas >= 20) ? kVisSmemHash : (bitmap_bytes <= (8ull << 30) ? kVisGlobalBitmap : kVisGlobalHash);
+    int vis = (smem_hash <= ix->smem_optin && ctas >= 20) ? kVisSmemHash
+            : ((bitmap_bytes <= (32ull << 30) && !ix->bitmap_oom) ? kVisGlobalBitmap : kVisGlobalHash);
     if (ix->visited_mode == 1) vis = kVisSmemHash;
     if (ix->visited_mode == 2) vis = kVisGlobalBitmap;
     if (ix->visited_mode == 3) vis = kVisGlobalHash;
@@ -368,7 +371,17 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
         merge_smem = (total * 12 + 8 * 4 + 15) & ~15ull;     // global ids u64 + distance words u32 per candidate, 8 list lengths
     }
     auto ctas_for = [](uint64_t smem) { return std::min<uint64_t>(32, (227ull * 1024) / (smem + 1024)); };
-    const int vis = plan_visited(ix, ef);
+    int vis = plan_visited(ix, ef);
+    if (vis == kVisGlobalBitmap && ix->visited_mode == 0) {
+        // reserve the bitmaps now; if the device cannot hold them, fall back to the hash (whose footprint does not grow with n)
+        const uint64_t resident0 = std::min<uint64_t>(nq, 32ull * ix->num_sms);
+        const uint64_t need0 = resident0 * ((g.n + 31) / 32);
+        if (need0 > ix->bitmap_buf.cap) {
+            cudaError_t eb = ix->bitmap_buf.reserve(need0);
+            if (eb == cudaErrorMemoryAllocation) { cudaGetLastError(); ix->bitmap_oom = true; vis = plan_visited(ix, ef); }
+            else { ZV_CUDA(eb); ZV_CUDA(cudaMemsetAsync(ix->bitmap_buf.p, 0, ix->bitmap_buf.cap * sizeof(uint32_t), s)); }
+        }
+    }
     const uint64_t res_cap = (static_cast<uint64_t>(ef) + 1) & ~1ull;
     // global modes: the popped-key list moves to per-CTA global scratch when it would cost residency (see the kernel)
     const bool res_global = vis != kVisSmemHash && ctas_for(smem_lists + merge_smem) < 32;

@@ -221,7 +221,12 @@ ZVDB_API int zvdb_sync_device(zvdb_index *ix);
  *           2 = the vector rows of a pop that wait for a later gather batch, 3 = the adjacency rows of the neighbours
  *           a pop evaluates (one of them is usually the next pop), 4 = both.
  * bit 11:   zvdb_search_batch with page-locked caller buffers: 0 = the kernel reads the queries from and writes the
- *           results to host memory directly (no copies), 1 = stage through device buffers (chunked copy pipeline). */
+ *           results to host memory directly (no copies), 1 = stage through device buffers (chunked copy pipeline).
+ * bit 12:   sharded step as round 1's three launches (search, flag kernel, merge kernel); bit 13: fused sharded step
+ *           through result blocks + release flags instead of 128-byte records.
+ * bits 14-15: the latency form of the search, one CTA of 8 warps per query (small batches, the single
+ *           search(query, k) call; result-identical): 0 = automatic (plain batches of at most 4 x SM count queries),
+ *           1 = never, 2 = whenever the shape fits its shared memory. */
 ZVDB_API int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant);
 
 /* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */

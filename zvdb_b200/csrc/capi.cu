@@ -405,7 +405,9 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     // Automatic while every query of the batch finds a resident CTA at once -- with the per-slot adjacency cache when that
     // fits (82 KB per query at ef = 64, m = 16: 2 per SM), without it otherwise (3 per SM) -- beyond that the one-warp
     // kernel's throughput wins (profiles/r02_c5_team_sweep.jsonl). team_mode 1 / 2 = never / whenever the shape fits.
-    if (!fx && n_peers == 0 && g.n > 0 && ef > 0 && ix->team_mode != 1) {
+    // (A forced visited-set or prefetch variant is a request for the one-warp kernel: those knobs exist only there.)
+    const bool team_auto = ix->team_mode == 0 && ix->visited_mode == 0 && ix->prefetch_mode == 0;
+    if (!fx && n_peers == 0 && g.n > 0 && ef > 0 && (team_auto || ix->team_mode == 2)) {
         const uint64_t team_cap = team_cand_cap(ef, g.m);     // one slot per (pop, neighbour position), and the final sort's scratch
         const uint64_t smem_plain = team_smem_bytes(team_cap, ef, hash_words, static_cast<uint32_t>(cpl), g.m, false);
         const uint64_t smem_cache = team_smem_bytes(team_cap, ef, hash_words, static_cast<uint32_t>(cpl), g.m, true);
@@ -426,7 +428,6 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
             }
             p.slots = static_cast<uint32_t>(slots); p.hash_words = static_cast<uint32_t>(hash_words);
             p.cand_cap = static_cast<uint32_t>(team_cap);
-            p.prefetch = getenv("ZVDB_TEAM_NOSHARE") ? 4u : 0u;   // (experiment)
             e = launch_team(g.metric, cpl, adjc, p, static_cast<unsigned>(nq), static_cast<size_t>(adjc ? smem_cache : smem_plain), s);
             ix->launches++;
             ZV_CUDA(e);

@@ -4,26 +4,28 @@
 // src/hnsw.zig:201-224, distance :182-192, result sort :227-233) -- bit for bit, held to the same oracle -- for the
 // small batches of BASELINE configs[4] and the reference's own call pattern, one search(query, k) at a time
 // (benchmarks/shared_benchmarks.zig:104-109). There a lone warp is bound by its own instruction chain: ~380
-// dependent instructions and two memory trips per pop, 1.9 us per pop on an otherwise empty B200
+// dependent instructions and two memory trips per pop, 1.6-1.9 us per pop on an otherwise empty B200
 // (profiles/r02_k1_ncu_nq1.md). This kernel spends a whole CTA on the query to shorten that chain, not to add
 // throughput. Per pop, on the critical path: ONE memory trip (the neighbours' rows), one half-warp reduction, ONE
 // CTA barrier, one 24-way minimum.
-//   * Every candidate ever pushed sits in an append-only shared-memory array; a popped slot is blanked. The
-//     candidate SET is all that matters: keys are the strict total order (distance, id), so the pop sequence
-//     equals the one-warp kernel's and the oracle's. The next pop is min(minimum of the older candidates, the <= m
-//     keys this pop pushed): the scan of the older ones runs WHILE this pop's rows are in flight, only the new keys
-//     meet it after the barrier.
+//   * Candidate slots are static: slot 0 is the entry point, pop t owns slots [1 + 16 t, 17 + 16 t) (m = 16), one per
+//     neighbour position, in shared memory; never-pushed and popped slots read ~0. Nothing on a pop's path allocates.
+//     The candidate SET is all that matters: keys are the strict total order (distance, id), so the pop sequence
+//     equals the one-warp kernel's and the oracle's. The next pop is min(minimum of the older slots, the <= m keys
+//     this pop pushed): the scan of the older ones runs WHILE this pop's rows are in flight, only its per-warp
+//     minima and the new keys meet after the barrier.
 //   * The <= 16 neighbours of a pop are evaluated together: half-warp h takes neighbour h, each lane loads two
-//     16-byte chunks per 128 floats of the row; the visited test (shared-memory hash, one lane per neighbour) and
-//     the slot allocation run while the rows are in flight. Rows of already-visited neighbours are fetched in vain:
-//     bandwidth is not what a small batch is short of.
-//   * The adjacency row of every evaluated neighbour is requested with its vector row (cp.async into a staging
-//     line) and kept in shared memory beside the candidate it belongs to, so a pop finds its neighbour ids on chip:
-//     the dependent adjacency fetch of the one-warp kernel is gone. (When ef * m lists do not fit, the row is read
-//     from global memory at the pop, as before.)
+//     16-byte chunks per 128 floats of the row; the visited test (shared-memory hash, one lane per neighbour) runs
+//     while the rows are in flight. Rows of already-visited neighbours are fetched in vain: bandwidth is not what
+//     a small batch is short of.
+//   * The adjacency row of every evaluated neighbour is requested with its vector row (cp.async straight into the
+//     neighbour's slot), so a pop finds its neighbour ids on chip: the dependent adjacency fetch of the one-warp
+//     kernel is gone. (When ef * m rows do not fit in shared memory, the row is read from global memory at the pop.)
 // Distance bits: lane j of a half-warp plays lanes j and j+16 of the one-warp kernel (two accumulators, same
 // chunk order), adds the two partial sums -- the first butterfly level, xor 16 -- and finishes with the xor 8, 4,
 // 2, 1 levels inside the half-warp: the same operands in the same tree as rows_distance / row_distance.
+// Measured (profiles/r02_c5_team_sweep.jsonl, 1M x 128, reference graph): one query, 64 pops: 56 us against 100 us for
+// the one-warp kernel; 10 pops (the reference's search(q, 10)): 15 us against 28 us.
 #pragma once
 #include "search_kernel.cuh"
 
@@ -154,7 +156,7 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
     }
     __syncthreads();
 
-    uint32_t np = 0, par = 0, nfresh = 0;                           // pops, exchange parity (uniform over the CTA); nodes this lane marked visited
+    uint32_t np = 0, nev = 1, par = 0;                              // pops, nodes visited, exchange parity (all uniform over the CTA)
     for (;;) {                                                      // hnsw.zig:211; cur_key / cur_slot = the candidate just popped (:212)
         if (tid == 0) { res[np] = cur_key; cand[cur_slot] = ~0ull; }                       // :214
         const uint32_t base_slot = 1u + np * MP;                    // this pop's slots; everything below them is older
@@ -163,12 +165,12 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
 
         for (uint32_t base = 0; base < MP; base += kTeamRows) {     // :216, 16 neighbours per pass, one per half-warp
             const uint32_t pos = base + half, slot = base_slot + pos;
-            const uint32_t *__restrict__ cur_adj = ADJC ? cadj + cur_slot * m : p.adj + static_cast<size_t>(cur) * m;
             uint32_t nb = kInvalidId;
-            if (pos < m) nb = ADJC ? cur_adj[pos] : __ldg(cur_adj + pos);
+            if (pos < m) nb = ADJC ? cadj[cur_slot * m + pos] : __ldg(p.adj + static_cast<size_t>(cur) * m + pos);
             const bool valid = nb != kInvalidId;
             const bool active = __any_sync(kFullMask, valid);       // (per warp) some half of this warp has a neighbour in this pass
             float4 vlo[CPL], vhi[CPL];
+            bool fresh = false;
             if (active) {
                 half_row_load<CPL, METRIC>(vlo, vhi, arena, p.row_chunks, valid ? nb : cur, j);   // (padding: a hot, valid row)
                 if (ADJC && valid) {                                // the neighbour's own adjacency row, in the same trip, straight into its slot
@@ -178,42 +180,21 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
                 }
+                if (j == 0 && valid) fresh = visited_insert(table, p.slots, nb);              // :217, :221 -- while the rows are in flight
             }
-            bool fresh = false;
-            if (active && j == 0 && valid) fresh = visited_insert(table, p.slots, nb);        // :217, :221 -- while the rows are in flight
-            nfresh += fresh;
             if (base == 0) {
-                // The minimum of the OLDER candidates (every slot below this pop's; the popped one excluded by its slot: its
-                // blanking store may still be on its way), also while the rows are in flight. A node of the reference's graph
-                // has few neighbours, so most warps have no row to evaluate: when at least half the warps are idle in this
-                // pass they share the scan and the busy ones skip it -- the busy warps are the pop's critical path.
-                uint32_t pos16 = kInvalidId;
-                if (lane < kTeamRows && lane < m) pos16 = ADJC ? cur_adj[lane] : __ldg(cur_adj + lane);
-                const uint32_t vmask = __ballot_sync(kFullMask, pos16 != kInvalidId);
-                const uint32_t busy = (vmask | (vmask >> 1)) & 0x5555u;                       // bit 2w: warp w has a row in pass 0
-                const uint32_t n_idle = kTeamWarps - __popc(busy);
-                const bool share = n_idle >= kTeamWarps / 2 && !(p.prefetch & 4u);
+                // The minimum of the OLDER candidates (every slot below this pop's; the popped one excluded by value: its blanking
+                // store may still be on its way), also while the rows are in flight. No warp-wide operation may sit between the
+                // visited test and this loop: lanes 0 and 16 are still in their CAS loops, and a vote here would make the other
+                // thirty wait for them (measured: +23 % per pop).
                 uint64_t best = ~0ull; uint32_t best_i = 0;
-                auto fold = [&](uint64_t key, uint32_t i) { if (key < best && i != cur_slot) { best = key; best_i = i; } };
-                auto scan = [&](uint32_t i, const uint32_t step) {   // four independent loads per round, then the compares
-                    for (; i < base_slot; i += 4u * step) {
-                        const uint32_t i1 = i + step, i2 = i1 + step, i3 = i2 + step;
-                        const uint64_t k0 = cand[i];
-                        const uint64_t k1 = i1 < base_slot ? cand[i1] : ~0ull;
-                        const uint64_t k2 = i2 < base_slot ? cand[i2] : ~0ull;
-                        const uint64_t k3 = i3 < base_slot ? cand[i3] : ~0ull;
-                        fold(k0, i); fold(k1, i1); fold(k2, i2); fold(k3, i3);
-                    }
-                };
-                if (!share) scan(tid, kTeamThreads);
-                else if (!active) scan(__popc(~busy & 0x5555u & ((1u << (2u * warp)) - 1u)) * 32u + lane, n_idle * 32u);
-                if (share && active) {
-                    if (lane == 0) wkey[par * kTeamWarps + warp] = ~0ull;
-                } else {
-                    const uint64_t wk = warp_min_key(best);
-                    const uint32_t owner = __ffs(__ballot_sync(kFullMask, best == wk)) - 1u;
-                    if (lane == owner) { wkey[par * kTeamWarps + warp] = wk; wslot[par * kTeamWarps + warp] = best_i; }
+                for (uint32_t i = tid; i < base_slot; i += kTeamThreads) {
+                    const uint64_t key = cand[i];
+                    if (key < best && key != cur_key) { best = key; best_i = i; }
                 }
+                const uint64_t wk = warp_min_key(best);
+                const uint32_t owner = __ffs(__ballot_sync(kFullMask, best == wk)) - 1u;
+                if (lane == owner) { wkey[par * kTeamWarps + warp] = wk; wslot[par * kTeamWarps + warp] = best_i; }
             }
             if (!active) continue;
             const float d = half_row_reduce<CPL, METRIC>(vlo, vhi, qlo, qhi);                 // :219
@@ -228,6 +209,7 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
             uint64_t key = ~0ull; uint32_t s = 0;
             if (t < MP) { key = cand[base_slot + t]; s = base_slot + t; }
             else if (t < MP + kTeamWarps) { key = wkey[par * kTeamWarps + t - MP]; s = wslot[par * kTeamWarps + t - MP]; }
+            nev += __popc(__ballot_sync(kFullMask, t < MP && key != ~0ull));                  // nodes this pop marked visited
             if (key < kbest) { kbest = key; sbest = s; }
         }
         if (np >= p.ef) break;
@@ -238,8 +220,6 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
     }
 
     // ---- result: stable sort of the popped entries by distance over pop order (hnsw.zig:227-233) ----
-    nfresh = __reduce_add_sync(kFullMask, nfresh);
-    if (lane == 0 && nfresh) atomicAdd(visited, nfresh);
     __syncthreads();
     uint64_t *sorted = cand;                                        // the candidates are dead now
     const uint32_t p2 = next_pow2(np);
@@ -260,7 +240,7 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
     if (tid == 0) {
         p.counts[q] = nres;
         if (p.pops) p.pops[q] = np;
-        if (p.evals) p.evals[q] = visited[0] + (p.seeds ? __ldg(p.seeds + q).z : 0u);
+        if (p.evals) p.evals[q] = nev + (p.seeds ? __ldg(p.seeds + q).z : 0u);
     }
 }
 

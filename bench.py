@@ -346,6 +346,46 @@ def time_k4(torch, h, dq0, nq, k, args, stream, reps=3):
             "note": "3xTF32 issues three MMA products per algorithmic product; the roofline fraction in SURVEY 8d's terms is the algorithmic one"}
 
 
+def small_batch(torch, h, args, X, dq1, Q1, k, ef, stream, O, kw):
+    """BASELINE configs[4] at its latency end, on the index of this line: batches of 1 and 64 queries, device time per launch of the
+    one-warp-per-query kernel K1 (zvdb_set_kernel_variant bits 14-15 = 1) and of the one-CTA-per-query kernel K1L (= 2; what a batch
+    this small runs on by default), successive launches on successive queries; K1L's rows of the first launch against the oracle."""
+    dev = dq1.device
+    dim = dq1.shape[1]
+    out = {"ef": ef, "k": k, "kernels": {"k1": "search_layer0_kernel (one warp per query)", "k1l": "search_team_kernel (one CTA of 8 warps per query)"}}
+    for bs in (1, 64):
+        o_ids = torch.empty((64 * bs, k), dtype=torch.int64, device=dev)
+        o_dist = torch.empty((64 * bs, k), dtype=torch.float32, device=dev)
+        o_cnt = torch.empty(64 * bs, dtype=torch.int32, device=dev)
+        row = {}
+        for name, variant in (("k1", 1 << 14), ("k1l", 2 << 14)):
+            h.set_kernel_variant(variant)
+            def launch(i):
+                off = (i % 64) * bs
+                h.search_batch_device(dq1.data_ptr() + off * dim * 4, bs, k, ef, o_ids.data_ptr() + off * k * 8, o_dist.data_ptr() + off * k * 4,
+                                      o_cnt.data_ptr() + off * 4, stream=stream)
+            for i in range(8):
+                launch(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(128):
+                launch(i)
+            b.record(); torch.cuda.synchronize()
+            row[name + "_device_us"] = round(a.elapsed_time(b) / 128 * 1e3, 2)
+        if O is not None:                       # K1L was the last to write slices 0..63
+            adj, _ = h.export_layer(0)
+            chk = 64 * bs
+            det = O.search_graph(X, adj, Q1[:chk], ef, k, dist_mode=O.DIST_TREE, heap_mode=O.HEAP_DET, **kw)
+            mask = np.arange(k)[None, :] < det["counts"][:, None]
+            row["k1l_bit_exact_vs_oracle"] = bool(np.array_equal(o_cnt.cpu().numpy().view(np.uint32), det["counts"]) and
+                                                  np.array_equal(o_ids.cpu().numpy().view(np.uint64)[mask], det["ids"].astype(np.uint64)[mask]) and
+                                                  np.array_equal(o_dist.cpu().numpy().view(np.uint32)[mask], det["dist"].view(np.uint32)[mask]))
+        out[f"nq_{bs}"] = row
+    h.set_kernel_variant(args.variant)
+    return out
+
+
 def throughput_track(torch, zvdb_b200, args, X, dq0, gt, stream, dev, row_bytes, log):
     """The regime in which K1 really is HBM-bound: the same kernel, same rows, same queries on a graph that reaches
     every row (search-driven incremental builder, <= M per node, entry 0), ef sweep 32..512. QPS from CUDA events
@@ -789,6 +829,9 @@ def run_ours(args):
     # ---- N=1 extras carried by the default line: K4 (exact k-NN) timing and the throughput track -------------------
     k4 = None
     track = None
+    small = None
+    if world == 1 and not args.no_track and not args.shard_gen and nq >= 4096 and not args.descent:
+        small = small_batch(torch, h, args, X, dq[1], Qs[1], k, ef, stream, O, kw)
     if world == 1 and not args.no_track and not args.no_recall and not args.shard_gen:
         k4 = time_k4(torch, h, dq[0], nq, k, args, stream)
         track = throughput_track(torch, zvdb_b200, args, X, dq[0], gt, stream, dev, row_bytes, log)
@@ -832,6 +875,8 @@ def run_ours(args):
         line["k4"] = k4
     if track:
         line["throughput_track"] = track
+    if small:
+        line["small_batch"] = small
     emit(line)
     if world > 1:
         dist.barrier()

@@ -135,6 +135,30 @@ def test_search_kernels_fit_their_register_budget_without_spills(zv):
             assert int(reg) <= 64, f"{name}: {reg} registers, 32 one-warp CTAs per SM need <= 64"
 
 
+def test_team_kernel_fits_its_residency_without_spills(zv):
+    """K1L (one CTA of 256 threads per query, search_team_kernel.cuh): no instantiation spills, and the 128-d ones fit the
+    register budget the launch rule counts on (capi.cu launch_search: three CTAs per SM at one 16-byte chunk pair per
+    lane -> 256 x 3 threads x <= 80 registers; two per SM up to 512-d -> <= 128). The m = 16 instantiations with the
+    on-chip adjacency cache copy adjacency rows with cp.async (LDGSTS in the SASS)."""
+    import re
+    import shutil
+    import subprocess
+    from zvdb_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    rows = re.findall(r"Function (\S*search_team_kernel\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert len(rows) == 5 * 3 * 3, f"{len(rows)} search_team_kernel instantiations (expected CPL x METRIC x {{plain, cached, cached m=16}})"
+    for name, reg, stack in rows:
+        m = re.search(r"search_team_kernelILi(\d+)ELi(\d)ELb([01])ELi(\d+)E", name)      # <CPL, METRIC, ADJC, MC>
+        assert m, name
+        cpl = int(m.group(1))
+        assert int(stack) == 0, f"{name} spills ({stack} bytes of stack)"
+        assert int(reg) <= (80 if cpl == 1 else 128 if cpl <= 4 else 255), f"{name}: {reg} registers"
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN4zvdb18search_team_kernelILi1ELi0ELb1ELi16EEEvNS_12SearchParamsE", _lib.LIB_PATH],
+                          capture_output=True, text=True).stdout
+    assert "LDGSTS" in sass and "CREDUX" in sass and "FFMA2" in sass, "K1L m=16: cp.async / REDUX / packed FMA not found"
+
+
 def test_library_sass_holds_the_blackwell_instructions_the_design_claims(zv):
     """DESIGN.md's claims about the machine code, checked on the built library: the exact k-NN kernel issues 5th-gen
     tensor-core MMAs on CTA pairs with TMA loads and TMEM reads (UTCHMMA.2CTA, UTMALDG.2D.2CTA, UTCBAR multicast commits,

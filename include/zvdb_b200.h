@@ -224,9 +224,10 @@ ZVDB_API int zvdb_sync_device(zvdb_index *ix);
  *           results to host memory directly (no copies), 1 = stage through device buffers (chunked copy pipeline).
  * bit 12:   sharded step as round 1's three launches (search, flag kernel, merge kernel); bit 13: fused sharded step
  *           through result blocks + release flags instead of 128-byte records.
- * bits 14-15: the latency form of the search, one CTA of 8 warps per query (small batches, the single
- *           search(query, k) call; result-identical): 0 = automatic (plain batches of at most 4 x SM count queries),
- *           1 = never, 2 = whenever the shape fits its shared memory. */
+ * bits 14-15: the latency form of the search, one CTA per query (small batches, the single search(query, k) call;
+ *           result-identical): 0 = automatic (plain batches whose queries are all resident at once: teams of 8 warps up
+ *           to 2-3 per SM, teams of 4 warps up to 6 per SM), 1 = never, 2 = teams of 8 warps whenever the shape fits their
+ *           shared memory, 3 = teams of 4 warps. */
 ZVDB_API int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant);
 
 /* Number of CUDA kernels this library has launched on behalf of `ix` since creation. */

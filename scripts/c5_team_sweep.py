@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """C5 (BASELINE configs[4]) A/B: the one-warp-per-query kernel K1 against the one-CTA-per-query latency form K1L
-(zvdb_set_kernel_variant bits 14-15 = 1 / 2) over the batch sizes where they compete, 1M x 128, on the reference
+(zvdb_set_kernel_variant bits 14-15 = 1 / 2; 3 = K1L with teams of 4 warps) over the batch sizes where they compete, 1M x 128, on the reference
 graph and on the incremental quality graph. Device time per launch (CUDA events, successive launches take successive
 slices of a 65 536-query pool so a launch never repeats the previous one's queries) and the host-call time of
 search_batch on pageable numpy buffers. Results of both kernels are compared row for row. JSON lines.
@@ -14,7 +14,7 @@ from zvdb_b200 import builder
 dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream().cuda_stream
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
-NEVER, ALWAYS = 1 << 14, 2 << 14
+NEVER, ALWAYS, HALF = 1 << 14, 2 << 14, 3 << 14
 n, dim, k, m = 1_000_000, 128, 10, 16
 X = np.random.default_rng(1).standard_normal((n, dim), dtype=np.float32)
 Qall = np.random.default_rng(2).standard_normal((65536, dim), dtype=np.float32)
@@ -47,7 +47,7 @@ for graph in (("reference", "incremental") if which == "both" else (which,)):
         for nq in ([int(x) for x in os.environ["C5_NQ"].split(",")] if os.environ.get("C5_NQ") else (1, 8, 64, 148, 296, 592, 1024, 2048, 4096)):
             row = {"config": "C5", "graph": graph, "ef": ef, "nq": nq}
             keep = None
-            for name, variant in (("k1", NEVER), ("k1l", ALWAYS)):
+            for name, variant in (("k1", NEVER), ("k1l", ALWAYS), ("k1l_half", HALF)):
                 h.set_kernel_variant(variant)
                 row[name + "_device_ms"] = round(device_ms(h, nq, ef, 200 if nq <= 296 else 50), 5)
                 torch.cuda.synchronize()

@@ -137,8 +137,8 @@ def test_search_kernels_fit_their_register_budget_without_spills(zv):
 
 def test_team_kernel_fits_its_residency_without_spills(zv):
     """K1L (one CTA of 256 threads per query, search_team_kernel.cuh): no instantiation spills, and the 128-d ones fit the
-    register budget the launch rule counts on (capi.cu launch_search: three CTAs per SM at one 16-byte chunk pair per
-    lane -> 256 x 3 threads x <= 80 registers; two per SM up to 512-d -> <= 128). The m = 16 instantiations with the
+    register budget the launch rule counts on (capi.cu launch_search: three 256-thread or six 128-thread CTAs per SM at one
+    16-byte chunk pair per lane -> 768 threads x <= 80 registers; two / four per SM up to 512-d -> <= 128). The m = 16 instantiations with the
     on-chip adjacency cache copy adjacency rows with cp.async (LDGSTS in the SASS)."""
     import re
     import shutil
@@ -147,14 +147,15 @@ def test_team_kernel_fits_its_residency_without_spills(zv):
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     out = subprocess.run([cuobjdump, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
     rows = re.findall(r"Function (\S*search_team_kernel\S*):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
-    assert len(rows) == 5 * 3 * 3, f"{len(rows)} search_team_kernel instantiations (expected CPL x METRIC x {{plain, cached, cached m=16}})"
+    assert len(rows) == 5 * 3 * 4, f"{len(rows)} search_team_kernel instantiations (expected CPL x METRIC x {{plain, cached, cached m=16, half team}})"
     for name, reg, stack in rows:
-        m = re.search(r"search_team_kernelILi(\d+)ELi(\d)ELb([01])ELi(\d+)E", name)      # <CPL, METRIC, ADJC, MC>
+        m = re.search(r"search_team_kernelILi(\d+)ELi(\d)ELb([01])ELi(\d+)ELi(\d+)E", name)      # <CPL, METRIC, ADJC, MC, T>
         assert m, name
-        cpl = int(m.group(1))
+        cpl, threads = int(m.group(1)), int(m.group(5))
+        assert threads in (128, 256), name
         assert int(stack) == 0, f"{name} spills ({stack} bytes of stack)"
         assert int(reg) <= (80 if cpl == 1 else 128 if cpl <= 4 else 255), f"{name}: {reg} registers"
-    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN4zvdb18search_team_kernelILi1ELi0ELb1ELi16EEEvNS_12SearchParamsE", _lib.LIB_PATH],
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN4zvdb18search_team_kernelILi1ELi0ELb1ELi16ELi256EEEvNS_12SearchParamsE", _lib.LIB_PATH],
                           capture_output=True, text=True).stdout
     assert "LDGSTS" in sass and "CREDUX" in sass and "FFMA2" in sass, "K1L m=16: cp.async / REDUX / packed FMA not found"
 

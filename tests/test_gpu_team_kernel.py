@@ -4,8 +4,9 @@ zvdb_b200/csrc/search_team_kernel.cuh), called through the C ABI against the CPU
 K1L is what a small batch and the reference's own call pattern -- one search(query, k) at a time
 (benchmarks/shared_benchmarks.zig:104-109) -- run on; it must return what the one-warp kernel and the oracle
 return, bit for bit: ids, order, distance bits, result counts and the pop / evaluation counters
-(src/hnsw.zig:194-236). zvdb_set_kernel_variant bits 14-15 force it off (1) or on (2) so both kernels are held
-to the oracle on the same shapes, whatever the automatic batch-size rule picks.
+(src/hnsw.zig:194-236). zvdb_set_kernel_variant bits 14-15 force it off (1), on with teams of 8 warps (2) or on with
+teams of 4 warps (3: what batches too large for full teams to be resident run on), so every form is held to the oracle
+on the same shapes, whatever the automatic batch-size rule picks.
 """
 import numpy as np
 import pytest
@@ -13,7 +14,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
-TEAM_NEVER, TEAM_ALWAYS = 1 << 14, 2 << 14
+TEAM_NEVER, TEAM_ALWAYS, TEAM_HALF = 1 << 14, 2 << 14, 3 << 14   # one warp per query / teams of 8 warps / teams of 4 warps
 
 
 def _gauss(n, dim, seed):
@@ -31,7 +32,7 @@ def _bit_exact(zv, got, ref, k):
     assert np.all(ids[~mask] == zv.INVALID_ID)
 
 
-@pytest.mark.parametrize("team", [TEAM_NEVER, TEAM_ALWAYS])
+@pytest.mark.parametrize("team", [TEAM_NEVER, TEAM_ALWAYS, TEAM_HALF])
 @pytest.mark.parametrize("n,dim,m,k,ef", [
     (10000, 128, 16, 10, 10),     # the reference call, ef = k
     (10000, 128, 16, 10, 64),     # C5's operating point
@@ -96,7 +97,7 @@ def test_team_kernel_on_a_quality_graph(zv, oracle):
     builder.build_quality_graph(h, X, m, K=48)
     adj, _ = h.export_layer(0)
     Q = _gauss(120, dim, 246)
-    for team in (TEAM_NEVER, TEAM_ALWAYS):
+    for team in (TEAM_NEVER, TEAM_ALWAYS, TEAM_HALF):
         h.set_kernel_variant(team)
         for k, ef in ((10, 10), (10, 64), (10, 200)):
             got = h.search_batch(Q, k, ef, counters=True)
@@ -117,9 +118,9 @@ def test_automatic_choice_single_call_and_batch_sizes_agree(zv, oracle):
     ref = oracle.search_graph(X, adj, Q, 48, 10, dist_mode=oracle.DIST_TREE, heap_mode=oracle.HEAP_DET)
     full = h.search_batch(Q, 10, 48, counters=True)                  # 700 queries: the one-warp kernel
     _bit_exact(zv, full, ref, 10)
-    for variant in (0, TEAM_NEVER, TEAM_ALWAYS, TEAM_ALWAYS | 0x100, TEAM_ALWAYS | 0x400):   # automatic, off, on, on without / with every prefetch
+    for variant in (0, TEAM_NEVER, TEAM_ALWAYS, TEAM_HALF, TEAM_ALWAYS | 0x100, TEAM_ALWAYS | 0x400):   # automatic, off, teams of 8 / 4 warps, forced next to K1-only bits
         h.set_kernel_variant(variant)
-        for s, bs in ((0, 1), (1, 7), (8, 64), (100, 296), (0, 700)):
+        for s, bs in ((0, 1), (1, 7), (8, 64), (100, 296), (50, 600), (0, 700)):
             got = h.search_batch(Q[s:s + bs], 10, 48, counters=True)
             for a, b in zip(got, full):
                 assert np.array_equal(a.view(np.uint8), b[s:s + bs].view(np.uint8)), (variant, s, bs)
@@ -144,7 +145,7 @@ def test_team_kernel_after_the_descent(zv, oracle):
     lvl, ub, ua = h.export_upper_layers()
     up = (lvl, ub, ua, h.max_level, h.descent_start)
     h.set_descent(True)
-    for team in (TEAM_NEVER, TEAM_ALWAYS):
+    for team in (TEAM_NEVER, TEAM_ALWAYS, TEAM_HALF):
         h.set_kernel_variant(team)
         for k, ef in ((10, 10), (10, 64)):
             got = h.search_batch(Q, k, ef, counters=True)

@@ -277,40 +277,43 @@ static cudaError_t launch_descend(int metric, int cpl, const SearchParams &p, un
     }
 }
 
-// K1L, the latency form: one CTA of 8 warps per query (search_team_kernel.cuh)
-template <int CPL, int METRIC, bool ADJC, int MC>
+// K1L, the latency form: one CTA of 8 (or 4) warps per query (search_team_kernel.cuh)
+template <int CPL, int METRIC, bool ADJC, int MC, int T>
 static cudaError_t launch_team_inst3(const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
-    auto kern = search_team_kernel<CPL, METRIC, ADJC, MC>;
+    auto kern = search_team_kernel<CPL, METRIC, ADJC, MC, T>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
-    kern<<<grid, kTeamThreads, smem, s>>>(p);
+    kern<<<grid, T, smem, s>>>(p);
     return cudaGetLastError();
 }
-// m = 16 (BASELINE's M) with the adjacency cache is compiled with m as a constant; everything else reads m from the parameters
+// Full teams (256 threads): m = 16 (BASELINE's M) with the adjacency cache is compiled with m as a constant, everything else
+// reads m from the parameters. Half teams (128 threads) exist without the cache only: they are what a batch runs on that is too
+// large for full teams to be resident at once.
 template <int CPL, int METRIC>
-static cudaError_t launch_team_inst(bool adjc, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
-    if (adjc && p.m == 16) return launch_team_inst3<CPL, METRIC, true, 16>(p, grid, smem, s);
-    return adjc ? launch_team_inst3<CPL, METRIC, true, 0>(p, grid, smem, s) : launch_team_inst3<CPL, METRIC, false, 0>(p, grid, smem, s);
+static cudaError_t launch_team_inst(bool adjc, unsigned threads, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    if (threads == 128) return launch_team_inst3<CPL, METRIC, false, 0, 128>(p, grid, smem, s);
+    if (adjc && p.m == 16) return launch_team_inst3<CPL, METRIC, true, 16, 256>(p, grid, smem, s);
+    return adjc ? launch_team_inst3<CPL, METRIC, true, 0, 256>(p, grid, smem, s) : launch_team_inst3<CPL, METRIC, false, 0, 256>(p, grid, smem, s);
 }
 template <int METRIC>
-static cudaError_t launch_team_metric(int cpl, bool adjc, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+static cudaError_t launch_team_metric(int cpl, bool adjc, unsigned threads, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     switch (cpl) {
-        case 1: return launch_team_inst<1, METRIC>(adjc, p, grid, smem, s);
-        case 2: return launch_team_inst<2, METRIC>(adjc, p, grid, smem, s);
-        case 4: return launch_team_inst<4, METRIC>(adjc, p, grid, smem, s);
-        case 6: return launch_team_inst<6, METRIC>(adjc, p, grid, smem, s);
-        case 8: return launch_team_inst<8, METRIC>(adjc, p, grid, smem, s);
+        case 1: return launch_team_inst<1, METRIC>(adjc, threads, p, grid, smem, s);
+        case 2: return launch_team_inst<2, METRIC>(adjc, threads, p, grid, smem, s);
+        case 4: return launch_team_inst<4, METRIC>(adjc, threads, p, grid, smem, s);
+        case 6: return launch_team_inst<6, METRIC>(adjc, threads, p, grid, smem, s);
+        case 8: return launch_team_inst<8, METRIC>(adjc, threads, p, grid, smem, s);
     }
     return cudaErrorInvalidValue;
 }
 // adjc = every candidate's adjacency row kept in shared memory (no dependent adjacency fetch at a pop)
-static cudaError_t launch_team(int metric, int cpl, bool adjc, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+static cudaError_t launch_team(int metric, int cpl, bool adjc, unsigned threads, const SearchParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     switch (metric) {
-        case 0: return launch_team_metric<kMetricL2>(cpl, adjc, p, grid, smem, s);
-        case 1: return launch_team_metric<kMetricCos>(cpl, adjc, p, grid, smem, s);
-        default: return launch_team_metric<kMetricDot>(cpl, adjc, p, grid, smem, s);
+        case 0: return launch_team_metric<kMetricL2>(cpl, adjc, threads, p, grid, smem, s);
+        case 1: return launch_team_metric<kMetricCos>(cpl, adjc, threads, p, grid, smem, s);
+        default: return launch_team_metric<kMetricDot>(cpl, adjc, threads, p, grid, smem, s);
     }
 }
 
@@ -402,22 +405,32 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
     const uint64_t smem_lists = (((static_cast<uint64_t>(ef) + 1) & ~1ull) + cand_cap) * 8 + kPoolCap * 8 + 32 * 4 + kPoolCap * 4 + 16;
     const uint64_t smem_hash = smem_lists + slots * 4;
     // K1L: a small plain batch gets one CTA per query (search_team_kernel.cuh: the latency form, same results bit for bit).
-    // Automatic while every query of the batch finds a resident CTA at once -- with the per-slot adjacency cache when that
-    // fits (82 KB per query at ef = 64, m = 16: 2 per SM), without it otherwise (3 per SM) -- beyond that the one-warp
-    // kernel's throughput wins (profiles/r02_c5_team_sweep.jsonl). team_mode 1 / 2 = never / whenever the shape fits.
+    // Automatic while every query of the batch finds a resident CTA at once: full teams (256 threads) with the per-slot
+    // adjacency cache when that fits (82 KB per query at ef = 64, m = 16: 2 per SM), full teams without it (3 per SM), then
+    // half teams (128 threads, 7 per SM at 128-d); beyond that the one-warp kernel's throughput wins
+    // (profiles/r02_c5_team_sweep.jsonl). team_mode 1 / 2 / 3 = never / full teams whenever the shape fits / half teams.
     // (A forced visited-set or prefetch variant is a request for the one-warp kernel: those knobs exist only there.)
     const bool team_auto = ix->team_mode == 0 && ix->visited_mode == 0 && ix->prefetch_mode == 0;
-    if (!fx && n_peers == 0 && g.n > 0 && ef > 0 && (team_auto || ix->team_mode == 2)) {
-        const uint64_t team_cap = team_cand_cap(ef, g.m);     // one slot per (pop, neighbour position), and the final sort's scratch
-        const uint64_t smem_plain = team_smem_bytes(team_cap, ef, hash_words, static_cast<uint32_t>(cpl), g.m, false);
-        const uint64_t smem_cache = team_smem_bytes(team_cap, ef, hash_words, static_cast<uint32_t>(cpl), g.m, true);
-        const uint64_t regs_ctas = cpl <= 1 ? 3 : (cpl <= 4 ? 2 : 1);            // 256 threads x 62-78 / 80-128 / 164+ registers
-        auto resident = [&](uint64_t smem) { return std::min<uint64_t>(regs_ctas, (227ull * 1024) / (smem + 1024)) * ix->num_sms; };
-        const bool fits_cache = smem_cache <= ix->smem_optin, fits_plain = smem_plain <= ix->smem_optin;
+    if (!fx && n_peers == 0 && g.n > 0 && ef > 0 && (team_auto || ix->team_mode >= 2)) {
+        const uint32_t ucpl = static_cast<uint32_t>(cpl);
+        const uint64_t cap256 = team_cand_cap(ef, g.m, 256), cap128 = team_cand_cap(ef, g.m, 128);
+        const uint64_t smem_plain = team_smem_bytes(cap256, ef, hash_words, ucpl, g.m, false);
+        const uint64_t smem_cache = team_smem_bytes(cap256, ef, hash_words, ucpl, g.m, true);
+        const uint64_t smem_half = team_smem_bytes(cap128, ef, hash_words, ucpl, g.m, false);
+        const uint64_t regs256 = cpl <= 1 ? 3 : (cpl <= 4 ? 2 : 1);              // 256 threads x 62-78 / 80-128 / 164+ registers
+        const uint64_t regs128 = cpl <= 1 ? 7 : (cpl <= 2 ? 6 : (cpl <= 4 ? 4 : 2));   // 128 threads x 72 / 82 / 118 / 194 registers
+        auto resident = [&](uint64_t smem, uint64_t by_regs) { return std::min<uint64_t>(by_regs, (227ull * 1024) / (smem + 1024)) * ix->num_sms; };
+        const bool fits_cache = smem_cache <= ix->smem_optin, fits_plain = smem_plain <= ix->smem_optin, fits_half = smem_half <= ix->smem_optin;
         bool use = false, adjc = false;
-        if (ix->team_mode == 2) { use = fits_plain; adjc = fits_cache && (nq <= resident(smem_cache) || resident(smem_cache) >= resident(smem_plain)); }
-        else if (fits_cache && nq <= resident(smem_cache)) { use = true; adjc = true; }
-        else if (fits_plain && nq <= resident(smem_plain)) { use = true; }
+        unsigned threads = 256;
+        uint64_t team_cap = cap256, team_smem = smem_plain;
+        if (ix->team_mode == 3) { use = fits_half; threads = 128; }
+        else if (ix->team_mode == 2) { use = fits_plain; adjc = fits_cache && (nq <= resident(smem_cache, regs256) || resident(smem_cache, regs256) >= resident(smem_plain, regs256)); }
+        else if (fits_cache && nq <= resident(smem_cache, regs256)) { use = true; adjc = true; }
+        else if (fits_plain && nq <= resident(smem_plain, regs256)) { use = true; }
+        else if (fits_half && nq <= resident(smem_half, regs128)) { use = true; threads = 128; }
+        if (adjc) team_smem = smem_cache;
+        if (threads == 128) { team_cap = cap128; team_smem = smem_half; }
         if (use) {
             cudaError_t e;
             if (p.seeds) {                                    // K2 first (its seeds are per-handle scratch: ordered across streams)
@@ -428,7 +441,7 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
             }
             p.slots = static_cast<uint32_t>(slots); p.hash_words = static_cast<uint32_t>(hash_words);
             p.cand_cap = static_cast<uint32_t>(team_cap);
-            e = launch_team(g.metric, cpl, adjc, p, static_cast<unsigned>(nq), static_cast<size_t>(adjc ? smem_cache : smem_plain), s);
+            e = launch_team(g.metric, cpl, adjc, threads, p, static_cast<unsigned>(nq), static_cast<size_t>(team_smem), s);
             ix->launches++;
             ZV_CUDA(e);
             if (p.seeds) ZV_CUDA(cudaEventRecord(ix->bitmap_ev, s));
@@ -1501,8 +1514,8 @@ int zvdb_sync_device(zvdb_index *ix) {
 int zvdb_set_kernel_variant(zvdb_index *ix, uint32_t variant) {
     if (!ix) return fail(ZVDB_ERR_INVALID, "null index");
     const uint32_t width = variant & 3u, vis = (variant >> 2) & 3u, bfm = (variant >> 4) & 3u;
-    if (width > 2 || bfm > 2 || variant > 49151 || ((variant >> 8) & 7u) > 4)
-        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = accepted and ignored (round 1's load-width variants are gone: never faster in any automatically chosen mode), bits 2-3 = visited set 0 auto/1 shared-memory hash/2 global bitmap/3 global hash, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-10 = L2 prefetch 0 auto/1 off/2 rows/3 adjacency/4 both, bit 11 = stage page-locked host buffers through device copies, bit 12 = sharded step as three launches (search, flag, merge) instead of the fused one, bit 13 = fused step through result blocks + release flags instead of 128-byte records, bits 14-15 = one CTA per query for small batches 0 auto/1 never/2 whenever the shape fits");
+    if (width > 2 || bfm > 2 || variant > 65535 || ((variant >> 8) & 7u) > 4)
+        return fail(ZVDB_ERR_INVALID, "variant: bits 0-1 = accepted and ignored (round 1's load-width variants are gone: never faster in any automatically chosen mode), bits 2-3 = visited set 0 auto/1 shared-memory hash/2 global bitmap/3 global hash, bits 4-5 = brute force 0 auto/1 single CTA/2 CTA pair, bit 6 = brute-force TF32 filter, bit 7 = brute-force sorted-list epilogue, bits 8-10 = L2 prefetch 0 auto/1 off/2 rows/3 adjacency/4 both, bit 11 = stage page-locked host buffers through device copies, bit 12 = sharded step as three launches (search, flag, merge) instead of the fused one, bit 13 = fused step through result blocks + release flags instead of 128-byte records, bits 14-15 = one CTA per query for small batches 0 auto/1 never/2 full teams (256 threads) whenever the shape fits/3 half teams (128 threads)");
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->prefetch_mode = (variant >> 8) & 7u; ix->stage_host_buffers = (variant >> 11) & 1u; ix->legacy_exchange = (variant >> 12) & 1u; ix->exchange_blocks = (variant >> 13) & 1u;
     ix->team_mode = (variant >> 14) & 3u;

@@ -31,15 +31,16 @@
 
 namespace zvdb {
 
-constexpr uint32_t kTeamThreads = 256;   // 8 warps = 16 half-warps = 16 neighbour rows per pass
-constexpr uint32_t kTeamRows = 16;
+constexpr uint32_t kTeamThreads = 256;   // the full team: 8 warps = 16 half-warps = 16 neighbour rows per pass
 constexpr uint32_t kTeamWarps = kTeamThreads / 32;
+// A team of T threads (256, or 128 for batches too large for full teams to be resident at once) evaluates T / 16
+// neighbour rows per pass.
 
 // Candidate slots of a team: slot 0 is the entry point, pop t (0-based) owns slots [1 + t * MP, 1 + (t + 1) * MP), one per
-// neighbour position (MP = m padded to whole 16-neighbour passes): a slot is known before its neighbour's freshness is,
+// neighbour position (MP = m padded to whole passes of T / 16 neighbours): a slot is known before its neighbour's freshness is,
 // so nothing on a pop's path allocates. Even, and at least next_pow2(ef): the final sort reuses the array.
-__host__ __device__ inline uint64_t team_cand_cap(uint64_t ef, uint32_t m) {
-    const uint64_t mp = (m + kTeamRows - 1) / kTeamRows * kTeamRows;
+__host__ __device__ inline uint64_t team_cand_cap(uint64_t ef, uint32_t m, uint32_t threads) {
+    const uint64_t rows = threads / 16, mp = (m + rows - 1) / rows * rows;
     uint64_t p2 = 2;
     while (p2 < ef) p2 <<= 1;
     const uint64_t cap = 1 + ef * mp;
@@ -99,12 +100,13 @@ __device__ __forceinline__ uint64_t warp_min_key(uint64_t key) {
 }
 
 // MC = m when it is known at compile time (16: BASELINE's M), 0 = read it from the parameters.
-template <int CPL, int METRIC, bool ADJC, int MC>
-__global__ void __launch_bounds__(kTeamThreads, (CPL <= 2 ? 2 : 1))
+template <int CPL, int METRIC, bool ADJC, int MC, int T>
+__global__ void __launch_bounds__(T, (T == 256 ? (CPL <= 2 ? 2 : 1) : (CPL <= 4 ? 4 : 2)))
 search_team_kernel(const __grid_constant__ SearchParams p) {
+    constexpr uint32_t TT = T, TW = T / 32, TR = T / 16;            // threads, warps, rows (half-warps) per pass
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t m = MC ? static_cast<uint32_t>(MC) : p.m;
-    const uint32_t MP = (m + kTeamRows - 1u) / kTeamRows * kTeamRows;     // neighbour slots of a pop, padded to whole passes
+    const uint32_t MP = (m + TR - 1u) / TR * TR;                    // neighbour slots of a pop, padded to whole passes
     uint64_t *cand = reinterpret_cast<uint64_t *>(smem_raw);        // [cand_cap] candidate keys by slot (team_cand_cap); ~0 = never pushed, or popped
     uint64_t *res = cand + p.cand_cap;                              // [ef, even] popped keys in pop order
     uint64_t *wkey = res + ((p.ef + 1u) & ~1u);                     // [2][8] by pop parity: per-warp minima of the older candidates
@@ -122,9 +124,9 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
     // query -> shared memory once (it may live in page-locked HOST memory: every load is a PCIe read), then registers
     {
         const float *qp = p.queries + static_cast<size_t>(q) * p.dim;
-        for (uint32_t i = tid; i < 128u * CPL; i += kTeamThreads) qs[i] = i < p.dim ? qp[i] : 0.0f;
-        for (uint32_t i = tid; i < p.slots; i += kTeamThreads) table[i] = kInvalidId;
-        for (uint32_t i = tid; i < p.cand_cap; i += kTeamThreads) cand[i] = ~0ull;
+        for (uint32_t i = tid; i < 128u * CPL; i += TT) qs[i] = i < p.dim ? qp[i] : 0.0f;
+        for (uint32_t i = tid; i < p.slots; i += TT) table[i] = kInvalidId;
+        for (uint32_t i = tid; i < p.cand_cap; i += TT) cand[i] = ~0ull;
     }
     __syncthreads();
     Chunk2 qlo[CPL], qhi[CPL];
@@ -152,7 +154,7 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
         }
         cur_key = pack_key(d0, entry);
         if (tid == 0) { visited_insert(table, p.slots, entry); visited[0] = 1u; }
-        if (ADJC) for (uint32_t w = tid; w < m; w += kTeamThreads) cadj[w] = __ldg(p.adj + static_cast<size_t>(entry) * m + w);
+        if (ADJC) for (uint32_t w = tid; w < m; w += TT) cadj[w] = __ldg(p.adj + static_cast<size_t>(entry) * m + w);
     }
     __syncthreads();
 
@@ -163,7 +165,7 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
         ++np;
         const uint32_t cur = key_id(cur_key);
 
-        for (uint32_t base = 0; base < MP; base += kTeamRows) {     // :216, 16 neighbours per pass, one per half-warp
+        for (uint32_t base = 0; base < MP; base += TR) {           // :216, T / 16 neighbours per pass, one per half-warp
             const uint32_t pos = base + half, slot = base_slot + pos;
             uint32_t nb = kInvalidId;
             if (pos < m) nb = ADJC ? cadj[cur_slot * m + pos] : __ldg(p.adj + static_cast<size_t>(cur) * m + pos);
@@ -188,7 +190,7 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
                 // visited test and this loop: lanes 0 and 16 are still in their CAS loops, and a vote here would make the other
                 // thirty wait for them (measured: +23 % per pop).
                 uint64_t best = ~0ull; uint32_t best_i = 0;
-                for (uint32_t i = tid; i < base_slot; i += kTeamThreads) {
+                for (uint32_t i = tid; i < base_slot; i += TT) {
                     const uint64_t key = cand[i];
                     if (key < best && key != cur_key) { best = key; best_i = i; }
                 }
@@ -204,11 +206,11 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
         __syncthreads();                                            // the one barrier of a pop: pushed keys, adjacency rows and warp minima are visible
         // ---- next pop (:212): min(keys this pop pushed, minimum of the older candidates) ----
         uint64_t kbest = ~0ull; uint32_t sbest = 0;
-        for (uint32_t t0 = 0; t0 < MP + kTeamWarps; t0 += 32u) {
+        for (uint32_t t0 = 0; t0 < MP + TW; t0 += 32u) {
             const uint32_t t = t0 + lane;
             uint64_t key = ~0ull; uint32_t s = 0;
             if (t < MP) { key = cand[base_slot + t]; s = base_slot + t; }
-            else if (t < MP + kTeamWarps) { key = wkey[par * kTeamWarps + t - MP]; s = wslot[par * kTeamWarps + t - MP]; }
+            else if (t < MP + TW) { key = wkey[par * kTeamWarps + t - MP]; s = wslot[par * kTeamWarps + t - MP]; }
             nev += __popc(__ballot_sync(kFullMask, t < MP && key != ~0ull));                  // nodes this pop marked visited
             if (key < kbest) { kbest = key; sbest = s; }
         }
@@ -223,11 +225,11 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
     __syncthreads();
     uint64_t *sorted = cand;                                        // the candidates are dead now
     const uint32_t p2 = next_pow2(np);
-    for (uint32_t i = tid; i < p2; i += kTeamThreads)
+    for (uint32_t i = tid; i < p2; i += TT)
         sorted[i] = i < np ? ((res[i] & 0xFFFFFFFF00000000ull) | i) : ~0ull;
     bitonic_sort_u64(sorted, p2);
     const uint32_t nres = min(np, p.k);
-    for (uint32_t r = tid; r < p.k; r += kTeamThreads) {
+    for (uint32_t r = tid; r < p.k; r += TT) {
         const size_t o = static_cast<size_t>(q) * p.k + r;
         uint64_t oid = ~0ull; float od = 0.0f;
         if (r < nres) {

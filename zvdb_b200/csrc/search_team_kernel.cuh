@@ -26,6 +26,8 @@
 // 2, 1 levels inside the half-warp: the same operands in the same tree as rows_distance / row_distance.
 // Measured (profiles/r02_c5_team_sweep.jsonl, 1M x 128, reference graph): one query, 64 pops: 56 us against 100 us for
 // the one-warp kernel; 10 pops (the reference's search(q, 10)): 15 us against 28 us.
+// T = 128 is the same kernel with teams of 4 warps (8 neighbour rows per pass): slower per query (85 us), but seven fit an SM
+// where two or three full teams do -- what a batch of 450-1 036 queries runs on (1 024 queries: 129 us against 146 us).
 #pragma once
 #include "search_kernel.cuh"
 

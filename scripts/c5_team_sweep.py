@@ -15,7 +15,10 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream().cuda_stream
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 NEVER, ALWAYS, HALF = 1 << 14, 2 << 14, 3 << 14
-n, dim, k, m = 1_000_000, 128, 10, 16
+# shape overrides (defaults = BASELINE configs[4]): C5_DIM, C5_M, C5_K, C5_EFS ("10,64"), C5_METRIC (0 L2 / 1 cosine / 2 dot), C5_NQ ("1,64,...")
+n, dim, k, m = 1_000_000, int(os.environ.get("C5_DIM", 128)), int(os.environ.get("C5_K", 10)), int(os.environ.get("C5_M", 16))
+metric = int(os.environ.get("C5_METRIC", 0))
+efs = [int(x) for x in os.environ.get("C5_EFS", "10,64").split(",")]
 X = np.random.default_rng(1).standard_normal((n, dim), dtype=np.float32)
 Qall = np.random.default_rng(2).standard_normal((65536, dim), dtype=np.float32)
 dq = torch.from_numpy(Qall).to(dev)
@@ -39,13 +42,13 @@ def device_ms(h, nq, ef, reps):
 
 
 for graph in (("reference", "incremental") if which == "both" else (which,)):
-    h = zvdb_b200.HNSW(m, 200)
+    h = zvdb_b200.HNSW(m, 200, metric=metric)
     if graph == "reference": h.insert_batch(X)
     else: builder.build_quality_graph_incremental(h, X, m)
     h.sync_device()
-    for ef in (10, 64):
+    for ef in efs:
         for nq in ([int(x) for x in os.environ["C5_NQ"].split(",")] if os.environ.get("C5_NQ") else (1, 8, 64, 148, 296, 592, 1024, 2048, 4096)):
-            row = {"config": "C5", "graph": graph, "ef": ef, "nq": nq}
+            row = {"config": "C5", "graph": graph, "dim": dim, "m": m, "k": k, "metric": metric, "ef": ef, "nq": nq}
             keep = None
             for name, variant in (("k1", NEVER), ("k1l", ALWAYS), ("k1l_half", HALF)):
                 h.set_kernel_variant(variant)

@@ -115,8 +115,7 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
     float *qs = reinterpret_cast<float *>(wkey + 2 * kTeamWarps);   // [128 * CPL] the query, zero padded
     uint32_t *table = reinterpret_cast<uint32_t *>(qs + 128 * CPL); // [hash_words] exact visited set, open addressing
     uint32_t *wslot = table + p.hash_words;                         // [2][8] the slots of those minima
-    uint32_t *visited = wslot + 2 * kTeamWarps;                     // [4] nodes marked visited (summed up when the search is over)
-    uint32_t *cadj = visited + 4;                                   // ADJC: [cand_cap][m] adjacency row of every candidate slot
+    uint32_t *cadj = wslot + 2 * kTeamWarps + 4;                    // ADJC: [cand_cap][m] adjacency row of every candidate slot (16 bytes of padding before it)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, j = lane & 15u;
     const uint32_t half = warp * 2u + (lane >> 4);                  // the neighbour position of a pass this half-warp evaluates
@@ -155,7 +154,7 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
             entry = sd.x; d0 = __uint_as_float(sd.y);
         }
         cur_key = pack_key(d0, entry);
-        if (tid == 0) { visited_insert(table, p.slots, entry); visited[0] = 1u; }
+        if (tid == 0) visited_insert(table, p.slots, entry);
         if (ADJC) for (uint32_t w = tid; w < m; w += TT) cadj[w] = __ldg(p.adj + static_cast<size_t>(entry) * m + w);
     }
     __syncthreads();

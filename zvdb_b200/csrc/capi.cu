@@ -82,6 +82,9 @@ struct zvdb_index {
     cudaEvent_t bf_ev = nullptr;     // last K4 call: its per-handle scratch (operand splits, partial lists, segment table) is shared by every call
     unsigned char *h_stage = nullptr; // owned, page-locked + device-mapped: small pageable batches (the single search call) go through it
     size_t h_stage_cap = 0;
+    uint32_t *mailbox_dev = nullptr; // set around the single-query launch: device address of the staging block's completion word ...
+    uint32_t mailbox_seq = 0;        // ... the value the kernel writes there ...
+    bool mailbox_armed = false;      // ... and whether the launch took it (only the one-CTA-per-query kernel does)
     float *d_arena = nullptr;       // [cap_rows][row_floats]
     uint32_t *d_adj = nullptr;      // [cap_rows][m]
     uint64_t cap_rows = 0, n_dev = 0;
@@ -441,6 +444,7 @@ static int launch_search(zvdb_index *ix, const float *d_q, uint64_t nq, uint32_t
             }
             p.slots = static_cast<uint32_t>(slots); p.hash_words = static_cast<uint32_t>(hash_words);
             p.cand_cap = static_cast<uint32_t>(team_cap);
+            if (ix->mailbox_dev && nq == 1) { p.done_flag = ix->mailbox_dev; p.done_seq = ix->mailbox_seq; ix->mailbox_armed = true; }
             e = launch_team(g.metric, cpl, adjc, threads, p, static_cast<unsigned>(nq), static_cast<size_t>(team_smem), s);
             ix->launches++;
             ZV_CUDA(e);
@@ -1598,7 +1602,7 @@ int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_
     {
         auto up = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
         const size_t qb = up(nq * dim * sizeof(float)), ib = up(nq * k * sizeof(uint64_t)), db = up(nq * k * sizeof(float)), cb = up(nq * sizeof(uint32_t));
-        const size_t total = qb + ib + db + 3 * cb;
+        const size_t total = qb + ib + db + 3 * cb + 256;    // + the completion word of the single-query call
         if (!ix->stage_host_buffers && total <= (1u << 20)) {
             if (total > ix->h_stage_cap) {
                 if (ix->h_stage) { ZV_CUDA(cudaStreamSynchronize(ix->stream)); cudaFreeHost(ix->h_stage); ix->h_stage = nullptr; ix->h_stage_cap = 0; }
@@ -1608,14 +1612,27 @@ int zvdb_search_batch(zvdb_index *ix, const float *queries, uint64_t nq, uint32_
             }
             unsigned char *hb = ix->h_stage, *dbase = nullptr;
             ZV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&dbase), hb, 0));
-            const size_t o_ids = qb, o_dist = qb + ib, o_cnt = o_dist + db, o_pops = o_cnt + cb, o_evals = o_pops + cb;
+            const size_t o_ids = qb, o_dist = qb + ib, o_cnt = o_dist + db, o_pops = o_cnt + cb, o_evals = o_pops + cb, o_done = o_evals + cb;
             std::memcpy(hb, queries, nq * dim * sizeof(float));
+            // One query (the reference's own call): the kernel reports through a word of this block, written after its results
+            // (system-scope fence), and the call returns when the host sees it -- a few microseconds before the stream would
+            // report the kernel complete. The stream stays ordered: the next launch on it waits for this kernel as usual.
+            volatile uint32_t *done = reinterpret_cast<volatile uint32_t *>(hb + o_done);
+            ix->mailbox_armed = false;
+            if (nq == 1) { ix->mailbox_dev = reinterpret_cast<uint32_t *>(dbase + o_done); ix->mailbox_seq += 1; if (ix->mailbox_seq == 0) ix->mailbox_seq = 1; *done = 0; }
             rc = launch_search(ix, reinterpret_cast<const float *>(dbase), nq, k, ef, reinterpret_cast<uint64_t *>(dbase + o_ids),
                                reinterpret_cast<float *>(dbase + o_dist), reinterpret_cast<uint32_t *>(dbase + o_cnt),
                                pops ? reinterpret_cast<uint32_t *>(dbase + o_pops) : nullptr,
                                evals ? reinterpret_cast<uint32_t *>(dbase + o_evals) : nullptr, 1, 0, ix->stream);
+            ix->mailbox_dev = nullptr;
             if (rc) return rc;
-            ZV_CUDA(cudaStreamSynchronize(ix->stream));
+            bool seen = false;
+            if (ix->mailbox_armed) {
+                const uint32_t want = ix->mailbox_seq;
+                for (uint32_t spins = 0; spins < (1u << 24) && !(seen = (*done == want)); ++spins) {}
+                std::atomic_thread_fence(std::memory_order_acquire);   // the result words are read after the completion word
+            }
+            if (!seen) ZV_CUDA(cudaStreamSynchronize(ix->stream));   // (batches, the one-warp kernel, or a kernel that never reported: the stream says why)
             std::memcpy(ids, hb + o_ids, nq * k * sizeof(uint64_t));
             std::memcpy(dist, hb + o_dist, nq * k * sizeof(float));
             std::memcpy(counts, hb + o_cnt, nq * sizeof(uint32_t));

@@ -110,6 +110,11 @@ struct SearchParams {
     uint32_t *peer_sflags[8];    // peer g's slice flags [8] x pitch: slot r = last epoch whose slice r is in place
     const uint32_t *sflags;      // this rank's slice flags
     uint32_t sflag_pitch;
+    // Completion mailbox of the single-query call (search_team_kernel only; null = none): when the results of the launch's one
+    // query are written, done_seq goes into this word of the page-locked, device-mapped staging block the results went to, so
+    // the host call returns on seeing it instead of waiting for the stream to report the kernel's completion.
+    uint32_t *done_flag;
+    uint32_t done_seq;
 };
 
 enum : int { kMetricL2 = 0, kMetricCos = 1, kMetricDot = 2 };

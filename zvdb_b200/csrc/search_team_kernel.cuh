@@ -245,6 +245,13 @@ search_team_kernel(const __grid_constant__ SearchParams p) {
         if (p.pops) p.pops[q] = np;
         if (p.evals) p.evals[q] = nev + (p.seeds ? __ldg(p.seeds + q).z : 0u);
     }
+    if (p.done_flag) {                                              // single-query call: tell the waiting host thread (uniform branch)
+        __syncthreads();                                            // every thread's result stores happen before thread 0's fence
+        if (tid == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(p.done_flag) = p.done_seq;
+        }
+    }
 }
 
 }  // namespace zvdb
